@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the hot path (BASELINE.json: configs[1]).
+
+    python bench.py --gpus 1 --steps 2 --warmup 3                # our arm
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 3   # the reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                               # one replica of the workload per rank
+
+Workload "1b_lyrics_top_prior": SimplePrior (prior_1b_lyrics hparams, n_ctx=8192 override -> 8576
+positions incl. 384 lyric tokens), n_samples=16 per GPU, random-init synthetic weights, random labels
+and lyric tokens, fp16 sampling, temp 0.99.  One "step" = one full window: 384-token lyric prefill +
+8192 sampled music tokens for 16 samples.  metric = music tokens per second (prefill time included).
+
+value   : device-resident inputs, CUDA-event time of K windows, max over ranks
+e2e     : the public call SimplePrior.sample(...) with labels copied from pinned host memory and the
+          codes copied back to the host inside the timed region (plus NCCL scatter/gather for N > 1)
+roofline: the persistent decode kernel (one launch per token): algorithmic bytes per launch
+          (fp16 Conv1D weights + fp32 x_out + LN/bias + KV rows read + KV rows written, SURVEY.md
+          section 8d) / average launch duration from a pure-kernel pass, vs MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline: oracle (numpy fp32 restatement of the reference) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CTX = 8192
+N_SAMPLES = 16
+WORKLOAD = "1b_lyrics_top_prior_n_ctx8192_n_samples16"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-tokens", type=int, default=24, help="tokens per sample in the CPU baseline sample")
+    ap.add_argument("--small", action="store_true", help="tiny debug configuration (not a valid bench number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+def hps_pair(small):
+    from jukebox_b200.hparams import setup_hparams
+    if small:     # debug only: 16 layers (one prime layer), 256 music tokens; (n_ctx + 384) % 64 == 0
+        vq = setup_hparams("vqvae", dict(sample_length=128 * 256, restore_vqvae=""))
+        pr = setup_hparams("prior_1b_lyrics", dict(n_ctx=256, prior_depth=16, restore_prior=""))
+    else:
+        vq = setup_hparams("vqvae", dict(sample_length=1048576, restore_vqvae=""))
+        pr = setup_hparams("prior_1b_lyrics", dict(n_ctx=N_CTX, restore_prior=""))
+    return vq, pr
+
+
+def synth_fill(model, seed):
+    """random-init synthetic weights with O(1) activations (same scale rules as oracle/synth.py),
+    drawn on the GPU"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            last = name.split(".")[-1]
+            z = torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)
+            if p.dim() == 1:
+                if last == "weight" and "ln" in name.split(".")[-2]:
+                    z = 1.0 + 0.1 * z
+                else:
+                    z = 0.1 * z
+            elif last == "w":
+                z = z * ((1.5 if name.endswith("c_attn.w") else 1.0) / p.shape[0] ** 0.5)
+            elif "pos_emb" in name:
+                z = z * 0.5
+            elif p.dim() == 3:
+                z = z / (p.shape[1] * p.shape[2]) ** 0.5
+            elif p.dim() == 2:
+                z = z * (2.0 / p.shape[1] ** 0.5)
+            p.copy_(z.to(p.dtype))
+
+
+def build_prior(small, seed=0):
+    import torch
+    from jukebox_b200.make_models import make_vqvae, make_prior
+    vq_h, pr_h = hps_pair(small)
+    with torch.device("cuda"):
+        vqvae = make_vqvae(vq_h, "cuda")
+        prior = make_prior(pr_h, vqvae, "cuda")
+    synth_fill(prior, seed)
+    return prior
+
+
+def make_labels(prior, n, seed):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    ys = []
+    for i in range(n):
+        lyric = rng.randint(0, 79, size=prior.n_tokens).tolist()
+        ys.append(prior.labeller.get_y_from_ids(int(rng.randint(0, 7898)), [int(rng.randint(0, 604))], lyric,
+                                                180 * 44100, 0))
+    import torch
+    y = torch.from_numpy(np.stack(ys)).long()
+    y[:, 2] = int(prior.sample_length)
+    return y
+
+
+def algorithmic_bytes_per_window(prior, n):
+    """sum over the window's launches of bytes_step(t, n)"""
+    tr = prior.prior.transformer
+    W, L = tr.n_in, tr.n_ctx
+    l0 = tr._attn_mods[0]
+    S, M = l0.attn.n_state, l0.mlp.c_fc.n_out
+    bc = tr.block_ctx
+    P = l0.attn._prime_len if tr.prime_len else 0
+    w_bytes = 0
+    for blk in tr._attn_mods:
+        for c in (blk.attn.c_attn, blk.attn.c_proj, blk.mlp.c_fc, blk.mlp.c_proj):
+            w_bytes += c.w.numel() * 2 + c.b.numel() * 4
+        w_bytes += 4 * W * 4
+    w_bytes += prior.prior.bins * W * 4            # fp32 x_out, as the reference keeps it
+    row = 2 * S * 2                                 # one K row + one V row, fp16
+    total = 0
+    for p in range(L):
+        kv = 0
+        for blk in tr._attn_mods:
+            f = blk.attn_func
+            if f == 0:
+                kv += (p + 1) + 1
+            elif f == 1:
+                kv += (p % bc + 1) + 1
+            elif f == 2:
+                kv += (p // bc + 1) + 1
+            elif f == 3:
+                kv += (bc if p >= bc else 0) + 1
+            elif f == 7:
+                kv += min(p + 1, P) + (1 if p < P else 0)
+        total += w_bytes + n * kv * row
+    return total, w_bytes
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], 0, set()
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(prior_state, cfg, n, tokens, seed=0):
+    """oracle (numpy fp32 restatement of the reference's CA2D.sample body) on the host cores"""
+    import numpy as np
+    from oracle.transformer_np import PriorOracle
+    orc = PriorOracle(prior_state, cfg["input_dims"], cfg["bins"], cfg["width"], cfg["depth"], cfg["heads"],
+                      attn_order=12, blocks=cfg["blocks"], x_cond=True, y_cond=True, prime_len=cfg["prime_len"])
+    rng = np.random.RandomState(seed)
+    toks = rng.randint(0, 79, size=(n, tokens + 1))
+    yc = rng.standard_normal((n, 1, cfg["width"])).astype(np.float32)
+    xc = np.zeros((n, 1, cfg["width"]), np.float32)
+    orc.logits(toks, xc, yc, None, False, n_steps=1)           # warm-up step (BLAS threads, page-in)
+    t0 = time.time()
+    orc.logits(toks, xc, yc, None, False, n_steps=tokens)
+    dt = time.time() - t0
+    return n * tokens / dt, dt
+
+
+def oracle_state_from(prior):
+    sd = {k: v.detach().float().cpu().numpy() for k, v in prior.prior.state_dict().items()}
+    tr = prior.prior.transformer
+    cfg = dict(input_dims=tr.n_ctx, bins=prior.prior.bins, width=tr.n_in, depth=tr.n_depth, heads=tr.n_head,
+               blocks=tr.blocks, prime_len=tr.prime_len)
+    return sd, cfg
+
+
+def synth_oracle_state(small):
+    """reference arm without a GPU model: same shapes, numpy-generated weights"""
+    import numpy as np
+    from jukebox_b200.make_models import make_vqvae, make_prior
+    import torch
+    vq_h, pr_h = hps_pair(small)
+    with torch.device("meta"):
+        vqvae = make_vqvae(vq_h, "meta")
+        prior = make_prior(pr_h, vqvae, "meta")
+    rng = np.random.default_rng(0)
+    sd = {}
+    for k, v in prior.prior.state_dict().items():
+        shape = tuple(v.shape)
+        a = rng.standard_normal(shape, dtype=np.float32)
+        if len(shape) == 1:
+            a = (1.0 + 0.1 * a) if (k.endswith("weight") and "ln" in k) else 0.1 * a
+        elif k.endswith(".w"):
+            a *= (1.5 if k.endswith("c_attn.w") else 1.0) / np.sqrt(shape[0])
+        elif "pos_emb" in k:
+            a *= 0.5
+        else:
+            a *= 2.0 / np.sqrt(shape[-1])
+        sd[k] = a.astype(np.float32)
+    tr = prior.prior.transformer
+    cfg = dict(input_dims=tr.n_ctx, bins=prior.prior.bins, width=tr.n_in, depth=tr.n_depth, heads=tr.n_head,
+               blocks=tr.blocks, prime_len=tr.prime_len)
+    return sd, cfg
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sd, cfg = synth_oracle_state(args.small)
+    cores = os.cpu_count()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(sd, cfg, N_SAMPLES, args.cpu_tokens, seed=i)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = sum(N_SAMPLES * args.cpu_tokens for _ in vals) / sum(dt for _, dt in vals)
+    sample = f"{args.cpu_tokens} token positions x {N_SAMPLES} samples per step, fp32, positions 0..{args.cpu_tokens - 1}"
+    line = dict(metric="top_prior_tokens_per_sec", value=value, unit="tokens/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * sum(dt for _, dt in vals) / len(vals), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, n_ctx=N_CTX, n_samples=N_SAMPLES, small=bool(args.small)),
+                cpu_baseline=dict(value=value, unit="tokens/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from jukebox_b200 import build as jk_build
+    if not os.path.exists(os.path.join(ROOT, "jukebox_b200", "libjkb200.so")):
+        jk_build.build()
+
+    prior = build_prior(args.small, seed=rank)
+    n = N_SAMPLES
+    tokens_per_window = n * prior.n_ctx
+    sample_kw = dict(fp16=True, temp=0.99, chunk_size=32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # conditioning for all ranks lives on rank 0's host; every rank needs its own slice
+    y_all_host = make_labels(prior, n * world, seed=1234).pin_memory()
+
+    def window_e2e():
+        """public API with host buffers: labels H2D (+ NCCL scatter), sample, codes D2H (+ gather)"""
+        if world > 1:
+            y_all = y_all_host.cuda(non_blocking=True) if rank == 0 else torch.empty_like(y_all_host, device="cuda")
+            dist.broadcast(y_all, 0)
+            y = y_all[rank * n:(rank + 1) * n].contiguous()
+        else:
+            y = y_all_host.cuda(non_blocking=True)
+        z = prior.sample(n_samples=n, z=None, z_conds=None, y=y, **sample_kw)
+        if world > 1:
+            out = [torch.empty_like(z) for _ in range(world)] if rank == 0 else None
+            dist.gather(z, out, 0)
+            z = torch.cat(out) if rank == 0 else z
+        return z.cpu()
+
+    y_dev = y_all_host[rank * n:(rank + 1) * n].cuda()
+    with torch.no_grad():
+        x_cond, y_cond, prime = prior.get_cond(None, y_dev)
+        z_in, x_cond_full = prior.prior_preprocess([prime], [None, x_cond])
+
+    def window_resident():
+        z = prior.prior.primed_sample(n, z_in, x_cond_full, y_cond, fp16=True, temp=0.99, chunk_size=32)
+        return prior.prior_postprocess(z)
+
+    import io
+    import contextlib
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with quiet:
+        for _ in range(max(args.warmup, 3) if not args.small else args.warmup):
+            window_resident()
+    # ---- value: K windows, device-resident inputs ---------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    with quiet:
+        for _ in range(args.steps):
+            window_resident()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_value = float(ms)
+    # ---- e2e: K windows through the public API with host buffers --------------------------------
+    with quiet:
+        window_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    with quiet:
+        for _ in range(args.steps):
+            z_host = window_e2e()
+    e1.record()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall_e2e * 1e3], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2[1])      # host-side wall time of the call, barrier to barrier (includes the D2H)
+    clocks = sampler.stop() if sampler else None
+    # ---- roofline: pure kernel pass (one launch per token, teacher-forced, logits every step) ---
+    eng = prior.prior._engine(n)
+    L = prior.prior.input_dims
+    toks = torch.randint(0, prior.prior.bins, (n, L), device="cuda")
+    lbuf = torch.empty(n, prior.prior.bins, device="cuda")
+    yc2 = y_cond.float().contiguous().view(n, -1)
+    prior.prior.transformer.del_cache()
+    for _ in range(8):
+        eng.step(n, tokens=toks, y_cond=yc2, x_cond=x_cond_full, logits=lbuf)
+    eng.reset(0)
+    barrier()
+    e0.record()
+    for _ in range(L):
+        eng.step(n, tokens=toks, y_cond=yc2, x_cond=x_cond_full, logits=lbuf)
+    e1.record()
+    barrier()
+    kern_ms = e0.elapsed_time(e1)
+    eng.reset(0)
+    total_bytes, w_bytes = algorithmic_bytes_per_window(prior, n)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = total_bytes / (kern_ms * 1e-3) / 1e9
+    roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                kernel="jk_decode_step_kernel", launches=L, avg_launch_us=1e3 * kern_ms / L,
+                algorithmic_bytes_per_launch=total_bytes / L, weight_bytes_per_launch=w_bytes,
+                peak_source="MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * tokens_per_window * args.steps / (ms_value * 1e-3)
+    e2e_v = world * tokens_per_window * args.steps / (ms_e2e * 1e-3)
+    line = dict(metric="top_prior_tokens_per_sec", value=value, unit="tokens/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_value / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="fp16", data="synthetic",
+                config=dict(workload=WORKLOAD if not args.small else "debug_small", n_ctx=prior.n_ctx,
+                            positions_per_window=L, n_samples_per_gpu=n, parallelism=f"replica x{world}",
+                            l2_policy="inputs larger than L2 (1.8 GB of weights streamed per token)",
+                            step="one full window: 384-token lyric prefill + n_ctx sampled tokens"),
+                e2e=dict(value=e2e_v, unit="tokens/s", h2d_bytes_per_step=int(y_all_host.numel() * 8),
+                         d2h_bytes_per_step=int(z_host.numel() * 8), ms_per_step=ms_e2e / args.steps,
+                         api="SimplePrior.sample(n_samples, z=None, z_conds=None, y, fp16=True, temp=0.99, chunk_size=32)"),
+                gpu_launches=int(args.steps * L), roofline=roof, clocks=clocks)
+    if not args.no_cpu_baseline:
+        sd, cfg = oracle_state_from(prior)
+        v, dt = cpu_baseline(sd, cfg, n, args.cpu_tokens)
+        line["cpu_baseline"] = dict(value=v, unit="tokens/s", cores=os.cpu_count(), kind="port",
+                                    sample=f"{args.cpu_tokens} token positions x {n} samples, fp32 oracle "
+                                           f"(numpy), positions 0..{args.cpu_tokens - 1}, {dt:.1f} s")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""Parameter containers with the reference's names (jukebox/transformer/ops.py) and the
+logit post-processing that stays in torch.
+
+Conv1D / LayerNorm here do NOT compute: at sampling time their parameters are packed into the
+decode engine (jukebox_b200/engine.py) and all arithmetic happens in libjkb200.so.
+"""
+import torch as t
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class LayerNorm(nn.Module):
+    """weight/bias holder for the fused LayerNorm (reference: ops.py:14-24, eps 1e-5)."""
+
+    def __init__(self, normalized_shape, eps=1e-5):
+        super().__init__()
+        self.normalized_shape = (int(normalized_shape),)
+        self.eps = eps
+        self.weight = nn.Parameter(t.ones(normalized_shape))
+        self.bias = nn.Parameter(t.zeros(normalized_shape))
+
+    def forward(self, x):
+        """fp32 rows on the GPU through jk_layernorm_f32 (used by the Conditioner)."""
+        from .._lib import lib, check, ptr, stream_ptr
+        x = x.float().contiguous()
+        y = t.empty_like(x)
+        rows = x.numel() // x.shape[-1]
+        check(lib().jk_layernorm_f32(ptr(x), ptr(self.weight.detach().float().contiguous()),
+                                     ptr(self.bias.detach().float().contiguous()), ptr(y), rows,
+                                     x.shape[-1], self.eps, stream_ptr()))
+        return y
+
+
+class Conv1D(nn.Module):
+    """w: [n_in, n_out] (transposed w.r.t. nn.Linear), b: [n_out]  - reference ops.py:83-96."""
+
+    def __init__(self, n_in, n_out, zero_out=False, init_scale=1.0):
+        super().__init__()
+        self.n_in, self.n_out = n_in, n_out
+        w = t.zeros(n_in, n_out) if zero_out else t.empty(n_in, n_out).normal_(std=0.02 * init_scale)
+        self.w = nn.Parameter(w)
+        self.b = nn.Parameter(t.zeros(n_out))
+
+    def forward(self, x):
+        raise RuntimeError("Conv1D is a parameter container; it runs inside the decode engine "
+                           "(Transformer.forward(sample=True)). No eager path exists.")
+
+
+def _convert_conv_weights_to_fp16(l):
+    if isinstance(l, Conv1D):
+        l.w.data = l.w.data.half()
+
+
+def _convert_conv_weights_to_fp32(l):
+    if isinstance(l, Conv1D):
+        l.w.data = l.w.data.float()
+
+
+def filter_logits(logits, top_k=0, top_p=0.0, filter_value=-float('Inf')):
+    """top-k / nucleus filtering of a logits tensor, semantics of the reference's
+    ops.py:113-142 (stays in torch on purpose: parity is defined on the logits, and the
+    sampling RNG stream is torch's)."""
+    out = logits.clone()
+    top_k = min(top_k, out.size(-1))
+    assert (top_k == 0) or (top_p == 0.0)
+    if top_k > 0:
+        kth = t.topk(out, top_k, dim=-1)[0][..., -1:]
+        out[out < kth] = filter_value
+    if top_p > 0.0:
+        srt, order = t.sort(out, descending=True, dim=-1)
+        cum = t.cumsum(F.softmax(srt, dim=-1), dim=-1)
+        drop = cum > top_p
+        drop[..., 1:] = drop[..., :-1].clone()
+        drop[..., 0] = 0
+        mask = t.zeros_like(out, dtype=t.bool).scatter_(dim=-1, index=order, src=drop)
+        out[mask] = filter_value
+    return out

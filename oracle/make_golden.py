@@ -251,7 +251,7 @@ def main():
                        encoder_dims=10)
     golden_transformer("order12", n_in=64, n_ctx=96, n_head=2, n_depth=16, attn_order=12, blocks=8, bs=2,
                        prime_len=12)
-    golden_transformer("order2_ragged", n_in=96, n_ctx=60, n_head=3, n_depth=6, attn_order=2, blocks=5, bs=5)
+    golden_transformer("order2_ragged", n_in=192, n_ctx=60, n_head=4, n_depth=6, attn_order=2, blocks=5, bs=5)
     golden_ca2d("xy", 48, 50, 64, 6, 2, 2, 4, True, True)
     golden_ca2d("plain", 48, 50, 64, 3, 1, 0, None, False, False)
     golden_ca2d("encdec_merged", 48, 50, 64, 8, 2, 6, 4, True, True, encoder_dims=10, merged_decoder=True)

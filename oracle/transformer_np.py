@@ -162,7 +162,8 @@ class TransformerOracle:
         self.res_scale = (1.0 / n_depth) if res_scale else 1.0
         self.reset()
 
-    def reset(self):
+    def reset(self, max_len=None):
+        self.max_len = self.n_ctx if max_len is None else min(self.n_ctx, max_len)
         self.K = [None] * self.n_depth
         self.V = [None] * self.n_depth
         self.enc_kv = [None] * self.n_depth
@@ -187,8 +188,8 @@ class TransformerOracle:
             qkv = conv1d(u, self._p(d, "attn.c_attn.w"), self._p(d, "attn.c_attn.b"), half)
             q, k, v = qkv[:, :S], qkv[:, S:2 * S], qkv[:, 2 * S:]
             if self.K[d] is None:
-                self.K[d] = np.zeros((bs, self.n_ctx, S), F32)
-                self.V[d] = np.zeros((bs, self.n_ctx, S), F32)
+                self.K[d] = np.zeros((bs, self.max_len, S), F32)
+                self.V[d] = np.zeros((bs, self.max_len, S), F32)
             pl = prime_len_padded(self.prime_len, self.blocks) if af == 7 else None
             if af != 7 or p < pl:          # prime_qkv appends only while cache shorter than _prime_len
                 self.K[d][:, p] = k
@@ -312,7 +313,7 @@ class PriorOracle:
         W = self.width
         if x_cond is None:
             x_cond = np.zeros((bs, 1, W), F32)
-        self.tr.reset()
+        self.tr.reset(max_len=n_steps)
         out = np.zeros((bs, n_steps, self.bins), F32)
         pos = self.sd["pos_emb.pos_emb"].astype(F32)
         emb = self.sd["x_emb.weight"].astype(F32)
