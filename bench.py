@@ -239,7 +239,9 @@ def synth_oracle_state(small):
 def run_reference(args, rank):
     if rank != 0:
         return
-    sd, cfg = synth_oracle_state(args.small)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        sd, cfg = synth_oracle_state(args.small)
     cores = os.cpu_count()
     vals = []
     for i in range(args.warmup + args.steps):
@@ -276,7 +278,9 @@ def main():
     if not os.path.exists(os.path.join(ROOT, "jukebox_b200", "libjkb200.so")):
         jk_build.build()
 
-    prior = build_prior(args.small, seed=rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # model-construction chatter must not precede the JSON line
+        prior = build_prior(args.small, seed=rank)
     n = N_SAMPLES
     tokens_per_window = n * prior.n_ctx
     sample_kw = dict(fp16=True, temp=0.99, chunk_size=32)

@@ -47,8 +47,10 @@ constexpr int kMaxSlots = 12;
 constexpr int kHeaderBytes = 1024;     // barriers + LN statistics
 constexpr int kLogitKT = 1024;         // K tile (floats) of the fp32 logits product
 constexpr int kLogitRowsPerChunk = 4;
-constexpr int kLogitRowsPerPass = 16;
+constexpr int kLogitRowsPerPass = 8;
 constexpr int kMaxSplit = 8;
+constexpr int kProfSlots = 1024;
+constexpr int kBarGroup = 12;           // CTAs per first-level barrier counter
 
 struct LayerDev {
     int attn_func;
@@ -71,6 +73,12 @@ struct EngineDev {
     unsigned long long stream_stride;
     __half *h, *qkv, *a, *x1, *g;   // [16][.] fp16 activations
     float* part;                    // split-KV partials [Bmax*H*kMaxSplit][dh_pad + 2]
+    unsigned* acnt;                 // [Bmax*H] merge tickets
+    long long* lnacc;               // [2*depth][16][2] fixed-point LayerNorm accumulators (sum, sumsq)
+    int split_rows;                 // attention: rows per part before a (sample, head) is split over CTAs
+    long long* prof2;               // [kProfSlots][8] intra-phase clock64 stamps of CTA 0 (tuning aid)
+    unsigned long long* prof3;      // [5][256][2] per-CTA barrier arrival / exit times of layer 1
+    unsigned long long* prof;       // [kProfSlots] phase timestamps of CTA 0 (globaltimer ns)
     unsigned* bar;
     unsigned* epoch;
     int* t;
@@ -92,17 +100,35 @@ struct StepArgs {
     long long logits_bstride, logits_tstride;
 };
 
+// The one dynamic shared-memory block of the decode kernel.  Every device function derives its
+// pointers from this symbol (never from pointer parameters): that is what lets the compiler emit
+// LDS/STS/ATOMS instead of generic LD/ST (measured: generic loads of the B fragments made the MMA loop
+// 6x slower than the tensor pipe allows).
+extern __shared__ __align__(1024) uint8_t jk_smem[];
+__device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(jk_smem); }
+__device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(jk_smem) + kMaxSlots; }
+__device__ __forceinline__ float* sm_stats() { return reinterpret_cast<float*>(jk_smem + 256); }
+__device__ __forceinline__ long long* sm_sacc() { return reinterpret_cast<long long*>(jk_smem + 512); }
+__device__ __forceinline__ uint8_t* sm_uni() { return jk_smem + kHeaderBytes; }
+
 struct Ring {
-    uint64_t* full;
-    uint64_t* empty;
-    uint8_t* base;
+    int base_off;          // byte offset of slot 0 inside jk_smem
     int nslot;
     int slot;
     uint32_t phase;
+    __device__ __forceinline__ uint64_t* full() const { return sm_full() + slot; }
+    __device__ __forceinline__ uint64_t* empty() const { return sm_empty() + slot; }
+    __device__ __forceinline__ uint8_t* data() const { return jk_smem + base_off + slot * kSlotBytes; }
     __device__ __forceinline__ void advance() {
         if (++slot == nslot) { slot = 0; phase ^= 1u; }
     }
 };
+
+#define STAMP(E_, slot_, i_)                                                                \
+    do {                                                                                    \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (slot_) < kProfSlots)                     \
+            (E_)->prof2[(size_t)(slot_) * 8 + (i_)] = clock64();                             \
+    } while (0)
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -111,16 +137,20 @@ __device__ __forceinline__ int kpc_of(int ncg) {
     return k < 8 ? 8 : k;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+// Grid-wide barrier through one L2 counter: release-add by one thread after a CTA barrier, acquire
+// polling, CTA barrier.  The CTA barriers make the pattern cumulative for the whole block, no separate
+// membar is needed.  Measured on B200 (tools/micro/ubench.cu): 2320 cycles = 1.18 us for 148 CTAs; a
+// two-level variant (group counters + top counter) measured 1.8-2.3 us in situ (two dependent
+// release/acquire round trips), so the flat counter stays.  `k` = global index of this barrier.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned k, int cta, int G) {
     consumer_sync();
     if (threadIdx.x == 0) {
-        __threadfence();
         red_release_add(bar, 1u);
+        const unsigned target = k * (unsigned)G;
         unsigned spins = 0;
         while ((int)(ld_acquire_u32(bar) - target) < 0) {
             if (++spins > (1u << 28)) __trap();
         }
-        __threadfence();
     }
     consumer_sync();
 }
@@ -138,70 +168,109 @@ __device__ __forceinline__ float quick_gelu_f(float x) {
 }
 
 // ---------------------------------------------------------------------------------------
-// activation staging: global fp16 [16][K] -> shared fp16 [16][K+8] (ldmatrix friendly),
-// optionally through LayerNorm (fp32 math, eps 1e-5; reference transformer/ops.py:14-24)
+// LayerNorm statistics travel with the activations: whoever WRITES a row block of the residual
+// stream also adds sum(x) and sum(x^2) of its columns into per-row 64-bit fixed-point accumulators
+// (exact integer adds => order independent => bit-reproducible), so the consuming GEMM can
+// normalise while it stages - no extra passes over the row, no extra grid barrier.
+//   sum  : x * 2^24 is an exact integer for every fp16 value
+//   sumsq: x^2 is exact in fp32; scaled by 2^16 and rounded per element (a pure function of x)
 // ---------------------------------------------------------------------------------------
-template <bool LN>
-__device__ void stage_acts(uint8_t* acts, float* stats, const __half* in, int K, int B,
-                           const float* gamma, const float* beta) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ long long fx_sum(float x) { return __float2ll_rn(x * 16777216.0f); }
+__device__ __forceinline__ long long fx_sq(float x) { return __float2ll_rn(x * x * 65536.0f); }
+__device__ __forceinline__ void red_add_s64(long long* p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+
+// activation staging: global fp16 [16][K] -> shared fp16 [16][K+8] (ldmatrix friendly), optionally
+// through LayerNorm (fp32 math, eps 1e-5; reference transformer/ops.py:14-24).  Each thread owns 8-column
+// vectors: 8 independent 16-byte loads in flight per batch, raw store, then (LN) a rolled in-place pass
+// over its own vectors.  Loops are deliberately NOT unrolled beyond that: the whole per-layer code must
+// stay inside the 32 KB instruction cache - an earlier fully unrolled build measured ~2.5 us of
+// instruction-fetch stalls in EVERY phase (profiles/ phase_profile_r01d.txt).
+__device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
+                                        const float* gamma, const float* beta, const long long* lnacc) {
+    const int tid = threadIdx.x;
+    uint8_t* acts = sm_uni();
+    float* stats = sm_stats();
     const int nvec = K >> 3;
     const int astride = (K + 8) * 2;
-    for (int idx = tid; idx < 16 * nvec; idx += kConsumers) {
-        int r = idx / nvec, v = idx - r * nvec;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < B) val = ldcg_u4(in + (size_t)r * K + v * 8);
-        *reinterpret_cast<uint4*>(acts + r * astride + v * 16) = val;
-    }
-    if (!LN) return;
-    consumer_sync();
-    for (int rr = 0; rr < 2; ++rr) {
-        int r = warp * 2 + rr;
-        if (r >= B) continue;
-        const uint8_t* row = acts + r * astride;
-        float s = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-            uint4 q = *reinterpret_cast<const uint4*>(row + v * 16);
-            const __half2* hp = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hp[e]); s += f.x + f.y; }
+    if (ln && tid < 16) {
+        float mean = 0.f, rstd = 0.f;
+        if (tid < B) {
+            // double only for the cancellation in E[x^2] - mean^2 (adds / muls; no double div or sqrt:
+            // those are kilobytes of library code in the instruction cache)
+            const double rk = (double)(1.0f / (float)K);    // K is a multiple of 16: exact for powers of two, 1e-7 rel otherwise
+            const double m = (double)__ldcg(lnacc + 16 * (2 * tid)) * (1.0 / 16777216.0) * rk;
+            double var = (double)__ldcg(lnacc + 16 * (2 * tid + 1)) * (1.0 / 65536.0) * rk - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            mean = (float)m;
+            rstd = 1.0f / sqrtf((float)var + 1e-5f);
         }
-        float mean = warp_sum(s) / (float)K;
-        float ss = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-            uint4 q = *reinterpret_cast<const uint4*>(row + v * 16);
-            const __half2* hp = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(hp[e]);
-                float dx = f.x - mean, dy = f.y - mean;
-                ss += dx * dx + dy * dy;
-            }
-        }
-        float var = warp_sum(ss) / (float)K;
-        if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = 1.0f / sqrtf(var + 1e-5f); }
+        stats[2 * tid] = mean;
+        stats[2 * tid + 1] = rstd;
     }
-    consumer_sync();
-    for (int v = tid; v < nvec; v += kConsumers) {
+#pragma unroll 1
+    for (int v0 = 0; v0 < nvec; v0 += kConsumers) {          // uniform trip count: the barrier below is CTA-wide
+        const int v = v0 + tid;
+        const bool act = v < nvec;
+        uint4 x[16];                                          // 16 independent 16-byte loads in flight
         float gm[8], bt[8];
-        *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-        *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-        *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-        *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-        for (int r = 0; r < B; ++r) {
-            uint4* p = reinterpret_cast<uint4*>(acts + r * astride + v * 16);
-            uint4 q = *p;
-            __half2* hp = reinterpret_cast<__half2*>(&q);
-            float mean = stats[2 * r], rstd = stats[2 * r + 1];
+        if (act) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(hp[e]);
-                f.x = (f.x - mean) * rstd * gm[2 * e] + bt[2 * e];
-                f.y = (f.y - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1];
-                hp[e] = __floats2half2_rn(f.x, f.y);
+            for (int r = 0; r < 16; ++r)
+                x[r] = (r < B) ? ldcg_u4(in + (size_t)r * K + v * 8) : make_uint4(0, 0, 0, 0);
+            if (ln) {
+                *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+                *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+                *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+                *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
             }
-            *p = q;
         }
+        if (ln && v0 == 0) consumer_sync();                  // row statistics are in shared memory (loads in flight)
+        if (act) {
+            if (ln) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    __half2* hp = reinterpret_cast<__half2*>(&x[r]);
+                    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 f = __half22float2(hp[e]);
+                        f.x = (f.x - mean) * rstd * gm[2 * e] + bt[2 * e];
+                        f.y = (f.y - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1];
+                        hp[e] = __floats2half2_rn(f.x, f.y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) *reinterpret_cast<uint4*>(acts + r * astride + v * 16) = x[r];
+        }
+    }
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// one ring slot worth of k-steps for this warp.  NCG (8-column groups of this CTA) is a template
+// parameter: with a run-time count the compiler serialised every LDS -> HMMA pair through one
+// register pair (tools/micro/ubench.cu: 4070 vs 1170 cycles for the K = 2048 loop).
+template <int NCG>
+__device__ __forceinline__ void mma_chunk(float (&acc)[8][4], uint32_t arow, uint32_t sl, int kk0, int nk, int warp) {
+#pragma unroll 4
+    for (int i = warp; i < nk; i += 8) {
+        uint32_t a[4];
+        ldsm4(a, arow + (kk0 + i) * 32);
+        uint2 b[NCG];
+#pragma unroll
+        for (int j = 0; j < NCG; ++j) b[j] = lds64(sl + ((i * NCG + j) << 8));
+#pragma unroll
+        for (int j = 0; j < NCG; ++j) mma_16816(acc[j], a, b[j].x, b[j].y);
     }
 }
 
@@ -210,14 +279,38 @@ __device__ void stage_acts(uint8_t* acts, float* stats, const __half* in, int K,
 // ---------------------------------------------------------------------------------------
 enum { EPI_QKV = 0, EPI_PROJ = 1, EPI_FC = 2, EPI_PROJ2 = 3 };
 
-template <bool LN, int EPI>
-__device__ void gemm_phase(const EngineDev* E, Ring& ring, uint8_t* uni, float* stats, const __half* in,
-                           int K, int N, int g0, int ncg, int B, const float* gamma, const float* beta,
-                           const float* bias) {
-    if (ncg == 0) return;
+struct GemmArgs {
+    const __half* in;
+    int K, N, g0, ncg, ln, epi, pslot;
+    const float *gamma, *beta, *bias;
+    const long long* ln_in;
+    long long* ln_out;
+};
+
+__device__ __noinline__ void gemm_phase(const EngineDev* E, Ring& ring_ref, int B, const GemmArgs& g_ref) {
+    uint8_t* uni = sm_uni();
+    if (g_ref.ncg == 0) return;
+    const GemmArgs g = g_ref;              // by value: keeps the arguments and the ring cursor in registers
+    Ring ring = ring_ref;                  // (through the reference they live in local memory = L2 round trips)
+    const int ncg = g.ncg;
+    STAMP(E, g.pslot, 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    stage_acts<LN>(uni, stats, in, K, B, gamma, beta);
+    const int K = g.K, N = g.N, epi = g.epi;
+    const int nc = ncg * 8;
+    const bool residual = (epi == EPI_PROJ || epi == EPI_PROJ2);
+    const __half* res_src = (epi == EPI_PROJ) ? E->h : E->x1;
+    __half* res_dst = (epi == EPI_PROJ) ? E->x1 : E->h;
+    // epilogue operands of this thread's first output element: issue the loads now, use them at the end
+    const bool has_e = tid < B * nc;
+    const int eb = has_e ? tid / nc : 0, ecc = has_e ? tid - eb * nc : 0;
+    float pre_bias = 0.f, pre_res = 0.f;
+    if (has_e) {
+        pre_bias = g.bias[g.g0 * 8 + ecc];
+        if (residual) pre_res = ld_half_cg(res_src + (size_t)eb * N + g.g0 * 8 + ecc);
+    }
+    stage_acts(g.in, K, B, g.ln, g.gamma, g.beta, g.ln_in);
     consumer_sync();
+    STAMP(E, g.pslot, 1);
 
     float acc[8][4];
 #pragma unroll
@@ -225,29 +318,34 @@ __device__ void gemm_phase(const EngineDev* E, Ring& ring, uint8_t* uni, float* 
     const int nkk = K >> 4;
     const int kpc = kpc_of(ncg);
     const int astride = (K + 8) * 2;
-    const uint8_t* arow = uni + (lane & 15) * astride + (lane >> 4) * 16;
+    const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
+    long long twait = 0;
+#pragma unroll 1
     for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {
         const int nk = min(kpc, nkk - kk0);
-        mbar_wait(&ring.full[ring.slot], ring.phase);
-        const uint8_t* sl = ring.base + ring.slot * kSlotBytes;
-        for (int i = warp; i < nk; i += 8) {
-            uint32_t a[4];
-            ldmatrix_x4(a, arow + (kk0 + i) * 32);
-            const uint2* bp = reinterpret_cast<const uint2*>(sl + (size_t)(i * ncg) * 256) + lane;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < ncg) {
-                    uint2 b = bp[j * 32];
-                    mma_16816(acc[j], a, b.x, b.y);
-                }
-            }
+        const long long tw0 = clock64();
+        mbar_wait(ring.full(), ring.phase);
+        twait += clock64() - tw0;
+        const uint32_t sl = smem_u32(ring.data()) + lane * 8;
+        switch (ncg) {
+            case 1: mma_chunk<1>(acc, arow, sl, kk0, nk, warp); break;
+            case 2: mma_chunk<2>(acc, arow, sl, kk0, nk, warp); break;
+            case 3: mma_chunk<3>(acc, arow, sl, kk0, nk, warp); break;
+            case 4: mma_chunk<4>(acc, arow, sl, kk0, nk, warp); break;
+            case 5: mma_chunk<5>(acc, arow, sl, kk0, nk, warp); break;
+            case 6: mma_chunk<6>(acc, arow, sl, kk0, nk, warp); break;
+            case 7: mma_chunk<7>(acc, arow, sl, kk0, nk, warp); break;
+            default: mma_chunk<8>(acc, arow, sl, kk0, nk, warp); break;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[ring.slot]);
+        if (lane == 0) mbar_arrive(ring.empty());
         ring.advance();
     }
+    STAMP(E, g.pslot, 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g.pslot < kProfSlots) E->prof2[(size_t)g.pslot * 8 + 6] = twait;
     consumer_sync();                       // everyone is done reading the staged activations
-    float* red = reinterpret_cast<float*>(uni);   // [8 warps][ncg][16][8]
+    float* red = reinterpret_cast<float*>(uni);   // [8 warps][ncg][16][8]  (<= 32 KB)
+    float* ov = reinterpret_cast<float*>(uni + 32768);   // [16][64] residual-stream outputs of this CTA
     {
         const int r0 = lane >> 2, c0 = (lane & 3) * 2;
 #pragma unroll
@@ -262,28 +360,44 @@ __device__ void gemm_phase(const EngineDev* E, Ring& ring, uint8_t* uni, float* 
         }
     }
     consumer_sync();
-    const int nc = ncg * 8;
+#pragma unroll 1
     for (int e = tid; e < B * nc; e += kConsumers) {
         const int b = e / nc, cc = e - b * nc;
         const int j = cc >> 3, col = cc & 7;
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += red[((w * ncg + j) * 16 + b) * 8 + col];
-        const int gc = g0 * 8 + cc;
-        const float y = h2f_round(s + bias[gc]);          // Conv1D output, rounded once to fp16
-        if (EPI == EPI_QKV) {
+        const int gc = g.g0 * 8 + cc;
+        const bool first = (e == tid);
+        const float y = h2f_round(s + (first ? pre_bias : g.bias[gc]));     // Conv1D output, rounded once to fp16
+        if (epi == EPI_QKV) {
             E->qkv[(size_t)b * N + gc] = __float2half_rn(y);
-        } else if (EPI == EPI_PROJ) {                      // x1 = fp16(h + a)
-            float hv = ld_half_cg(E->h + (size_t)b * N + gc);
-            E->x1[(size_t)b * N + gc] = __float2half_rn(hv + y);
-        } else if (EPI == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
+        } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
             E->g[(size_t)b * N + gc] = __float2half_rn(quick_gelu_f(y));
-        } else {                                           // h = fp16(x1 + m)
-            float xv = ld_half_cg(E->x1 + (size_t)b * N + gc);
-            E->h[(size_t)b * N + gc] = __float2half_rn(xv + y);
+        } else {
+            // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
+            const float base = first ? pre_res : ld_half_cg(res_src + (size_t)b * N + gc);
+            const float o = h2f_round(base + y);
+            res_dst[(size_t)b * N + gc] = __float2half_rn(o);
+            ov[b * 64 + cc] = o;
         }
     }
+    STAMP(E, g.pslot, 3);
     consumer_sync();                       // red region is reused by the next phase's staging
+    if (residual && g.ln_out) {
+        // statistics for the LayerNorm that will read these rows: warp w reduces rows 2w, 2w+1 of this
+        // CTA's columns in a fixed order (exact integer sums), one 64-bit red per row and moment
+#pragma unroll 1
+        for (int r = 2 * warp; r < 2 * warp + 2 && r < B; ++r) {
+            long long s1 = 0, s2 = 0;
+            for (int cc = lane; cc < nc; cc += 32) { const float o = ov[r * 64 + cc]; s1 += fx_sum(o); s2 += fx_sq(o); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            if (lane == 0) { red_add_s64(g.ln_out + 16 * (2 * r), s1); red_add_s64(g.ln_out + 16 * (2 * r + 1), s2); }
+        }
+        consumer_sync();                   // ov is reused
+    }
+    ring_ref = ring;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -315,209 +429,226 @@ __device__ __forceinline__ AttnGeom attn_geom(const EngineDev* E, const LayerDev
     return g;
 }
 
-__device__ __forceinline__ int attn_nsplit(const EngineDev* E, const LayerDev& LD, int B, int R) {
-    if (LD.attn_func == 1 || LD.attn_func == 2 || LD.attn_func == 3) return 1;
-    if (R <= 256) return 1;
-    int ns = E->G / (B * E->H);
-    ns = max(1, min(kMaxSplit, ns));
-    return ns;
+__device__ __host__ __forceinline__ int attn_tile_rows(int dhp) {
+    int r = 12288 / (dhp * 2);
+    return r < 1 ? 1 : (r > 64 ? 64 : r);
 }
 
-__device__ void attn_item(const EngineDev* E, const LayerDev& LD, uint8_t* uni, float* stats, int b, int h,
-                          int s, int ns, const AttnGeom& G) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// how many CTAs share one (sample, head): as few as keep every part inside ONE shared-memory tile
+// (2*TR cached rows), bounded by the grid
+__device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache) {
+    const int cap = 2 * attn_tile_rows(E->dh_pad);
+    int ns = (ncache + cap - 1) / cap;
+    ns = min(ns, E->G / (B * E->H));
+    return max(1, min(kMaxSplit, ns));
+}
+
+// One (sample, head, part) work item; q_len == 1 (reference factored_attention.py:82-133 and the
+// per-pattern sample branches :135-228).
+//   * the part's K and V rows are staged with cp.async - all rows in flight at once; a part that fits
+//     (<= 2*TR rows) is ONE tile, longer parts (dense / prime layers) run double-buffered TR-row tiles
+//   * scores: thread (row, slice) computes an eighth of a row's dot product, 3 shuffles finish it;
+//     s = fp16(fp16(q.k) * dh^-1/2) exactly as the reference rounds it
+//   * softmax is flash-style in fp32 (running max / sum, unnormalised P), P.V by one thread per
+//     output dimension; parts of one (sample, head) are merged by the last CTA to finish (atomic
+//     ticket), so the phase needs no extra grid barrier
+__device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_ref, int b, int h, int s, int ns,
+                                       const AttnGeom& G_ref, int pslot) {
+    uint8_t* uni = sm_uni();
+    float* stats = sm_stats();
+    const LayerDev LD = LD_ref;
+    const AttnGeom G = G_ref;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int dh = E->dh, dhp = E->dh_pad, S = E->S;
     const int nvec = dhp >> 3;
-    int LPR = 1;
-    while (LPR < nvec && LPR < 32) LPR <<= 1;
-    const int RPW = 32 / LPR;
-    const int grp = lane / LPR, li = lane % LPR;
-
-    float* qs = reinterpret_cast<float*>(uni);          // [dhp]
-    float* ks = qs + dhp;                               // [dhp] current token's k
-    float* vs = ks + dhp;                               // [dhp]
-    float* red = vs + dhp;                              // [8][dhp]
-    float* sc = red + 8 * dhp;                          // scores of this split
+    const int TR = attn_tile_rows(dhp);
+    const int tileB = (TR + 1) * dhp * 2;
+    float* qs = reinterpret_cast<float*>(uni + 4 * tileB);   // [dhp]
+    float* sc = qs + dhp;                                    // [2*TR + 2] scores of the tile
+    float* sp = sc + 2 * (TR + 1);                           // [2*TR + 2] exp(score - running max)
     const int qkv_stride = (LD.attn_func == 6) ? S : 3 * S;
     const __half* qrow = E->qkv + (size_t)b * qkv_stride + h * dh;
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
-    const bool writer = (s == ns - 1);
+    const bool last_part = (s == ns - 1);
+    const int R = G.R;
 
-    for (int d = tid; d < dhp; d += kConsumers) {
-        float q = 0.f, k = 0.f, v = 0.f;
-        if (d < dh) {
-            q = ld_half_cg(qrow + d);
-            if (LD.attn_func != 6) {
-                k = ld_half_cg(qrow + S + d);
-                v = ld_half_cg(qrow + 2 * S + d);
-                if (writer && G.wrow >= 0) {
-                    LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(k);
-                    LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(v);
-                }
+    if (R == 0) {   // prev-block attention inside the first block: keys/values are zeros -> output 0
+        for (int d = tid; d < dh; d += kConsumers) {
+            E->a[(size_t)b * S + h * dh + d] = __float2half_rn(0.f);
+            if (G.wrow >= 0) {
+                LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + S + d));
+                LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
             }
         }
-        qs[d] = q; ks[d] = k; vs[d] = v;
+        return;
     }
-    consumer_sync();
-    const int R = G.R;
-    if (R == 0) {   // prev-block attention inside the first block: keys/values are zeros -> output 0
-        for (int d = tid; d < dh; d += kConsumers) E->a[(size_t)b * S + h * dh + d] = __float2half_rn(0.f);
+    STAMP(E, pslot, 0);
+    const int ncache = R - (G.cur ? 1 : 0);               // rows that come from the cache
+    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
+    const __half* kbase = LD.kc + (cbase + G.base) * dhp;
+    const __half* vbase = LD.vc + (cbase + G.base) * dhp;
+    const bool one_shot = (i1 - i0) <= 2 * TR;
+    const int trows = one_shot ? 2 * TR : TR;
+    const int ntiles = one_shot ? 1 : (i1 - i0 + TR - 1) / TR;
+    const int voff = one_shot ? 2 * tileB : tileB;        // V buffer offset from the K buffer of a stage
+
+    auto issue_tile = [&](int ti) {
+        const int r0 = i0 + ti * trows, nr = max(0, min(trows, i1 - r0));
+        const uint32_t kd = smem_u32(uni + (one_shot ? 0 : (ti & 1) * 2 * tileB)), vd = kd + voff;
+        const __half* ks = kbase + (size_t)r0 * dhp;
+        const __half* vs = vbase + (size_t)r0 * dhp;
+#pragma unroll 2
+        for (int i = tid; i < nr * nvec; i += kConsumers) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + i * 16), "l"(ks + i * 8));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + i * 16), "l"(vs + i * 8));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_tile(0);
+    for (int d = tid; d < dhp; d += kConsumers) qs[d] = (d < dh) ? ld_half_cg(qrow + d) : 0.f;
+    if (!G.cur && G.wrow >= 0 && last_part) {   // patterns that do not attend the current token still cache it
+        for (int d = tid; d < dh; d += kConsumers) {
+            LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + S + d));
+            LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
+        }
+    }
+    // score mapping: SL lanes share a row (SL = 8 for every real head size)
+    int SL = 1;
+    while (SL < 8 && SL * 2 <= nvec) SL <<= 1;
+    const int rr = tid / SL, sl = tid % SL, RP = kConsumers / SL;
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[2] = {0.f, 0.f};                              // output dims tid and tid + 256
+#pragma unroll 1
+    for (int ti = 0; ti < ntiles; ++ti) {
+        if (ti + 1 < ntiles) {
+            issue_tile(ti + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const int r0 = i0 + ti * trows;
+        int nr = max(0, min(trows, i1 - r0));
+        __half* kt = reinterpret_cast<__half*>(uni + (one_shot ? 0 : (ti & 1) * 2 * tileB));
+        __half* vt = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(kt) + voff);
+        if (ti == ntiles - 1 && last_part && G.cur) {       // append the current token's k, v (from the QKV GEMM)
+            for (int d = tid; d < dhp; d += kConsumers) {
+                __half kh = __float2half_rn(0.f), vh = kh;
+                if (d < dh) {
+                    kh = __float2half_rn(ld_half_cg(qrow + S + d));
+                    vh = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
+                    if (G.wrow >= 0) {
+                        LD.kc[(cbase + G.wrow) * dhp + d] = kh;
+                        LD.vc[(cbase + G.wrow) * dhp + d] = vh;
+                    }
+                }
+                kt[nr * dhp + d] = kh;
+                vt[nr * dhp + d] = vh;
+            }
+            nr += 1;
+        }
+        consumer_sync();
+        STAMP(E, pslot, 1);
+        // ---- scores -------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int base = 0; base < nr; base += RP) {
+            const int r = base + rr;
+            float dot = 0.f;
+            if (r < nr) {
+#pragma unroll 1
+                for (int v = sl; v < nvec; v += SL) {
+                    const uint4 q4 = *reinterpret_cast<const uint4*>(kt + r * dhp + v * 8);
+                    const __half2* hp = reinterpret_cast<const __half2*>(&q4);
+                    const float4 qa = *reinterpret_cast<const float4*>(qs + v * 8);
+                    const float4 qb = *reinterpret_cast<const float4*>(qs + v * 8 + 4);
+                    const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
+                    const float2 f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
+                    dot += qa.x * f0.x + qa.y * f0.y + qa.z * f1.x + qa.w * f1.y;
+                    dot += qb.x * f2.x + qb.y * f2.y + qb.z * f3.x + qb.w * f3.y;
+                }
+            }
+            for (int o = SL >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (r < nr && sl == 0) sc[r] = h2f_round(h2f_round(dot) * E->scale2);
+        }
+        consumer_sync();
+        STAMP(E, pslot, 2);
+        if (nr > 0) {
+            float m_t = -INFINITY;
+#pragma unroll 1
+            for (int r = 0; r < nr; ++r) m_t = fmaxf(m_t, sc[r]);
+            const float m_new = fmaxf(m_run, m_t);
+            const float corr = expf(m_run - m_new);          // exp(-inf) = 0 on the first tile
+            for (int r = tid; r < nr; r += kConsumers) sp[r] = expf(sc[r] - m_new);
+            consumer_sync();
+            m_run = m_new;
+            float lt = 0.f, a0 = acc[0] * corr, a1 = acc[1] * corr;
+            const bool d1 = tid + kConsumers < dhp;
+            if (tid < dhp) {
+#pragma unroll 4
+                for (int r = 0; r < nr; ++r) {
+                    const float pr = sp[r];
+                    lt += pr;
+                    a0 += pr * __half2float(vt[r * dhp + tid]);
+                    if (d1) a1 += pr * __half2float(vt[r * dhp + tid + kConsumers]);
+                }
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < nr; ++r) lt += sp[r];
+            }
+            acc[0] = a0; acc[1] = a1;
+            l_run = l_run * corr + lt;
+        }
+        if (ti + 1 < ntiles) consumer_sync();                 // tile buffers and sc/sp are reused
+    }
+    STAMP(E, pslot, 3);
+    if (ns == 1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int d = tid + u * kConsumers;
+            if (d < dh) E->a[(size_t)b * S + h * dh + d] = __float2half_rn(acc[u] / l_run);
+        }
         consumer_sync();
         return;
     }
-    const int i0 = (int)(((long long)R * s) / ns), i1 = (int)(((long long)R * (s + 1)) / ns);
-    const int n = i1 - i0;
-    const int cur_idx = G.cur ? R - 1 : -1;
-    const __half* kbase = LD.kc + (cbase + G.base) * dhp;
-    const __half* vbase = LD.vc + (cbase + G.base) * dhp;
-
-    // ---- scores: s = fp16(fp16(q.k) * dh^-1/2) --------------------------------------------
-    for (int base = i0 + warp * RPW; base < i1; base += 8 * RPW) {
-        const int idx = base + grp;
-        float dot = 0.f;
-        if (idx < i1) {
-            if (idx == cur_idx) {
-                for (int v = li; v < nvec; v += LPR) {
+    // ---- split parts: publish the partial, the last finisher merges (flash-decoding merge) ----------
+    const int item = b * E->H + h;
+    float* part = E->part + ((size_t)(item * kMaxSplit + s)) * (dhp + 2);
+    if (tid == 0) { part[0] = m_run; part[1] = l_run; }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) dot += qs[v * 8 + e] * ks[v * 8 + e];
-                }
-            } else {
-                const __half* row = kbase + (size_t)idx * dhp;
-                for (int v = li; v < nvec; v += LPR) {
-                    uint4 q4 = __ldg(reinterpret_cast<const uint4*>(row + v * 8));
-                    const __half2* hp = reinterpret_cast<const __half2*>(&q4);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 f = __half22float2(hp[e]);
-                        dot += qs[v * 8 + 2 * e] * f.x + qs[v * 8 + 2 * e + 1] * f.y;
-                    }
-                }
-            }
-        }
-        for (int o = LPR >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (idx < i1 && li == 0) sc[idx - i0] = h2f_round(h2f_round(dot) * E->scale2);
+    for (int u = 0; u < 2; ++u) {
+        const int d = tid + u * kConsumers;
+        if (d < dhp) part[2 + d] = acc[u];
     }
     consumer_sync();
-    // ---- softmax statistics (fp32) ----------------------------------------------------------
-    float m = -INFINITY;
-    for (int i = tid; i < n; i += kConsumers) m = fmaxf(m, sc[i]);
-    m = warp_max(m);
-    if (lane == 0) stats[32 + warp] = m;
-    consumer_sync();
-    m = stats[32];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, stats[32 + w]);
-    float l = 0.f;
-    for (int i = tid; i < n; i += kConsumers) {
-        float e = expf(sc[i] - m);
-        sc[i] = e;
-        l += e;
-    }
-    l = warp_sum(l);
-    if (lane == 0) stats[40 + warp] = l;
-    consumer_sync();
-    l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) l += stats[40 + w];
-    if (ns == 1) {   // reference rounding: P = fp16(softmax)
-        for (int i = tid; i < n; i += kConsumers) sc[i] = h2f_round(sc[i] / l);
-        consumer_sync();
-    }
-    // ---- P.V ------------------------------------------------------------------------------
-    float acc[2][8];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
-    for (int base = i0 + warp * RPW; base < i1; base += 8 * RPW) {
-        const int idx = base + grp;
-        if (idx < i1) {
-            const float pw = sc[idx - i0];
-            if (idx == cur_idx) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    int v = li + u * LPR;
-                    if (v < nvec) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[u][e] += pw * vs[v * 8 + e];
-                    }
-                }
-            } else {
-                const __half* row = vbase + (size_t)idx * dhp;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    int v = li + u * LPR;
-                    if (v < nvec) {
-                        uint4 q4 = __ldg(reinterpret_cast<const uint4*>(row + v * 8));
-                        const __half2* hp = reinterpret_cast<const __half2*>(&q4);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float2 f = __half22float2(hp[e]);
-                            acc[u][2 * e] += pw * f.x;
-                            acc[u][2 * e + 1] += pw * f.y;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    for (int o = LPR; o < 32; o <<= 1) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[u][e] += __shfl_xor_sync(0xffffffffu, acc[u][e], o);
-    }
-    if (grp == 0) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            int v = li + u * LPR;
-            if (v < nvec) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) red[warp * dhp + v * 8 + e] = acc[u][e];
-            }
-        }
+    if (tid == 0) {      // acq_rel ticket: publishes this CTA's partial, acquires the others' for the merger
+        unsigned ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(E->acnt + item) : "memory");
+        stats[48] = (ticket == (unsigned)(ns - 1)) ? 1.f : 0.f;
+        if (ticket == (unsigned)(ns - 1)) E->acnt[item] = 0u;
     }
     consumer_sync();
-    if (ns == 1) {
+    if (stats[48] != 0.f) {
+        const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
+        float M = -INFINITY;
+        for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * (dhp + 2)));
+        float Lsum = 0.f;
+        for (int q = 0; q < ns; ++q)
+            Lsum += __ldcg(p0 + (size_t)q * (dhp + 2) + 1) * expf(__ldcg(p0 + (size_t)q * (dhp + 2)) - M);
         for (int d = tid; d < dh; d += kConsumers) {
             float o = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) o += red[w * dhp + d];
-            E->a[(size_t)b * S + h * dh + d] = __float2half_rn(o);
-        }
-    } else {
-        float* part = E->part + ((size_t)((b * E->H + h) * kMaxSplit + s)) * (dhp + 2);
-        if (tid == 0) { part[0] = m; part[1] = l; }
-        for (int d = tid; d < dhp; d += kConsumers) {
-            float o = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) o += red[w * dhp + d];
-            part[2 + d] = o;
+            for (int q = 0; q < ns; ++q)
+                o += __ldcg(p0 + (size_t)q * (dhp + 2) + 2 + d) * expf(__ldcg(p0 + (size_t)q * (dhp + 2)) - M);
+            E->a[(size_t)b * S + h * dh + d] = __float2half_rn(o / Lsum);
         }
     }
     consumer_sync();
-}
-
-__device__ void attn_merge(const EngineDev* E, int b, int h, int ns) {
-    const int dh = E->dh, dhp = E->dh_pad;
-    const float* part = E->part + ((size_t)((b * E->H + h) * kMaxSplit)) * (dhp + 2);
-    float M = -INFINITY;
-    for (int s = 0; s < ns; ++s) M = fmaxf(M, __ldcg(part + (size_t)s * (dhp + 2)));
-    float Lsum = 0.f;
-    for (int s = 0; s < ns; ++s)
-        Lsum += __ldcg(part + (size_t)s * (dhp + 2) + 1) * expf(__ldcg(part + (size_t)s * (dhp + 2)) - M);
-    for (int d = threadIdx.x; d < dh; d += kConsumers) {
-        float o = 0.f;
-        for (int s = 0; s < ns; ++s)
-            o += __ldcg(part + (size_t)s * (dhp + 2) + 2 + d) * expf(__ldcg(part + (size_t)s * (dhp + 2)) - M);
-        E->a[(size_t)b * E->S + h * dh + d] = __float2half_rn(o / Lsum);
-    }
+    STAMP(E, pslot, 6);
 }
 
 // ---------------------------------------------------------------------------------------
 // producer warp: walks this CTA's weight stream (and the logits rows) in consumption order
 // ---------------------------------------------------------------------------------------
-__device__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int c) {
+__device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int c) {
     if ((threadIdx.x & 31) != 0) return;
     const uint8_t* src = E->streams + (size_t)c * E->stream_stride + (size_t)E->soff[(size_t)c * (E->depth + 1)] * 16;
     for (int l = 0; l < E->depth; ++l) {
@@ -531,9 +662,9 @@ __device__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int
             for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {
                 const int nk = min(kpc, nkk - kk0);
                 const uint32_t bytes = (uint32_t)nk * ncg * 256u;
-                mbar_wait(&ring.empty[ring.slot], ring.phase ^ 1u);
-                mbar_expect_tx(&ring.full[ring.slot], bytes);
-                tma_bulk_g2s(ring.base + ring.slot * kSlotBytes, src, bytes, &ring.full[ring.slot]);
+                mbar_wait(ring.empty(), ring.phase ^ 1u);
+                mbar_expect_tx(ring.full(), bytes);
+                tma_bulk_g2s(ring.data(), src, bytes, ring.full());
                 src += bytes;
                 ring.advance();
             }
@@ -548,11 +679,11 @@ __device__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int
                 const int kt = min(kLogitKT, W - k0);
                 for (int r = pr; r < pe; r += kLogitRowsPerChunk) {
                     const int nr = min(kLogitRowsPerChunk, pe - r);
-                    mbar_wait(&ring.empty[ring.slot], ring.phase ^ 1u);
-                    mbar_expect_tx(&ring.full[ring.slot], (uint32_t)(nr * kt * 4));
+                    mbar_wait(ring.empty(), ring.phase ^ 1u);
+                    mbar_expect_tx(ring.full(), (uint32_t)(nr * kt * 4));
                     for (int i = 0; i < nr; ++i)
-                        tma_bulk_g2s(ring.base + ring.slot * kSlotBytes + i * kt * 4,
-                                     E->x_out + (size_t)(r + i) * W + k0, (uint32_t)(kt * 4), &ring.full[ring.slot]);
+                        tma_bulk_g2s(ring.data() + i * kt * 4, E->x_out + (size_t)(r + i) * W + k0,
+                                     (uint32_t)(kt * 4), ring.full());
                     ring.advance();
                 }
             }
@@ -562,7 +693,10 @@ __device__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int
 
 // fp32 logits: logits[b, r] = sum_k y[b, k] * x_out[r, k],  y = float(h) (+ cond)
 // (reference autoregressive.py:226-229: fp32 nn.Linear on the fp32 transformer output)
-__device__ void logits_phase(const EngineDev* E, const StepArgs& A, Ring& ring, uint8_t* uni, int c, int t) {
+__device__ __noinline__ void logits_phase(const EngineDev* E, const StepArgs& A_ref, Ring& ring_ref, int c, int t) {
+    uint8_t* uni = sm_uni();
+    const StepArgs A = A_ref;
+    Ring ring = ring_ref;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = E->lrow0[c], r1 = E->lrow0[c + 1];
     const int W = E->W, B = A.n;
@@ -575,15 +709,35 @@ __device__ void logits_phase(const EngineDev* E, const StepArgs& A, Ring& ring, 
         for (int k0 = 0; k0 < W; k0 += kLogitKT) {
             const int kt = min(kLogitKT, W - k0);
             consumer_sync();
-            for (int idx = tid; idx < 16 * kt; idx += kConsumers) {
-                int b = idx / kt, k = idx - b * kt;
-                float y = 0.f;
-                if (b < B) {
-                    y = ld_half_cg(E->h + (size_t)b * W + k0 + k);
-                    if (E->add_cond_after && A.x_cond)
-                        y += A.x_cond[((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + k0 + k];
+            {   // y = float(h) (+ cond): 8 halves per thread-iteration, loads batched 4 deep
+                const int nv = kt >> 3;
+                for (int idx0 = tid; idx0 < 16 * nv; idx0 += 4 * kConsumers) {
+                    uint4 hv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = idx0 + u * kConsumers;
+                        const int b = idx / nv, v = idx - b * nv;
+                        hv[u] = (idx < 16 * nv && b < B) ? ldcg_u4(E->h + (size_t)b * W + k0 + v * 8) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = idx0 + u * kConsumers;
+                        if (idx >= 16 * nv) continue;
+                        const int b = idx / nv, v = idx - b * nv;
+                        const __half2* hp = reinterpret_cast<const __half2*>(&hv[u]);
+                        float y[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hp[e]); y[2 * e] = f.x; y[2 * e + 1] = f.y; }
+                        if (b < B && E->add_cond_after && A.x_cond) {
+                            const float* cp = A.x_cond + ((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + k0 + v * 8;
+                            const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+                            y[0] += c0.x; y[1] += c0.y; y[2] += c0.z; y[3] += c0.w;
+                            y[4] += c1.x; y[5] += c1.y; y[6] += c1.z; y[7] += c1.w;
+                        }
+                        *reinterpret_cast<float4*>(ys + b * kt + v * 8) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4*>(ys + b * kt + v * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                    }
                 }
-                ys[b * kt + k] = y;
             }
             consumer_sync();
             const float* y0 = ys + (warp * 2) * kt;
@@ -593,8 +747,8 @@ __device__ void logits_phase(const EngineDev* E, const StepArgs& A, Ring& ring, 
                 const int r = pr + rc * kLogitRowsPerChunk;
                 if (r < pe) {
                     const int nr = min(kLogitRowsPerChunk, pe - r);
-                    mbar_wait(&ring.full[ring.slot], ring.phase);
-                    const float* wsl = reinterpret_cast<const float*>(ring.base + ring.slot * kSlotBytes);
+                    mbar_wait(ring.full(), ring.phase);
+                    const float* wsl = reinterpret_cast<const float*>(ring.data());
                     for (int k = lane * 4; k < kt; k += 128) {
                         float4 a0 = *reinterpret_cast<const float4*>(y0 + k);
                         float4 a1 = *reinterpret_cast<const float4*>(y1 + k);
@@ -608,7 +762,7 @@ __device__ void logits_phase(const EngineDev* E, const StepArgs& A, Ring& ring, 
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ring.empty[ring.slot]);
+                    if (lane == 0) mbar_arrive(ring.empty());
                     ring.advance();
                 }
             }
@@ -628,18 +782,12 @@ __device__ void logits_phase(const EngineDev* E, const StepArgs& A, Ring& ring, 
 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const EngineDev* __restrict__ E, StepArgs A) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + kMaxSlots;
-    float* stats = reinterpret_cast<float*>(smem + 256);    // [32] LN stats + [16] softmax scratch
-    uint8_t* uni = smem + kHeaderBytes;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int c = blockIdx.x;
     Ring ring;
-    ring.full = full; ring.empty = empty; ring.base = uni + E->uni_bytes; ring.nslot = E->nslot;
-    ring.slot = 0; ring.phase = 0;
+    ring.base_off = kHeaderBytes + E->uni_bytes; ring.nslot = E->nslot; ring.slot = 0; ring.phase = 0;
     if (tid == 0) {
-        for (int i = 0; i < E->nslot; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+        for (int i = 0; i < E->nslot; ++i) { mbar_init(sm_full() + i, 1); mbar_init(sm_empty() + i, 8); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -652,58 +800,122 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     const unsigned epoch0 = *reinterpret_cast<volatile const unsigned*>(E->epoch);
     unsigned nbar = 0;
     const int B = A.n, W = E->W, S = E->S, M = E->M, G = E->G;
-#define GRID_BARRIER() do { ++nbar; grid_barrier(E->bar, epoch0 + nbar * (unsigned)G); } while (0)
+#define GRID_BARRIER()                                                                     \
+    do {                                                                                   \
+        STAMP(E, (int)nbar, 4);                                                            \
+        if (tid == 0 && nbar >= 6 && nbar < 11) {                                          \
+            unsigned long long now_;                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
+            E->prof3[((nbar - 6) * 256 + c) * 2] = now_;                                   \
+        }                                                                                  \
+        ++nbar;                                                                            \
+        grid_barrier(E->bar, epoch0 + nbar, c, G);                                         \
+        if (tid == 0 && nbar >= 7 && nbar < 12) {                                          \
+            unsigned long long now_;                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
+            E->prof3[((nbar - 7) * 256 + c) * 2 + 1] = now_;                               \
+        }                                                                                  \
+        STAMP(E, (int)nbar - 1, 5);                                                        \
+        if (c == 0 && tid == 0 && nbar < (unsigned)kProfSlots) {                           \
+            unsigned long long now;                                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));                        \
+            E->prof[nbar] = now;                                                           \
+        }                                                                                  \
+    } while (0)
+    if (c == 0 && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        E->prof[0] = now;
+    }
 
     // ---- P0: embedding (autoregressive.py:177-197) or an externally embedded activation ------
-    for (int e = c * kConsumers + tid; e < B * W; e += G * kConsumers) {
-        const int b = e / W, col = e - b * W;
-        float x;
-        if (A.x_in) {
-            x = A.x_in[e];
-        } else {
-            if (t == 0) x = A.y_cond ? A.y_cond[e] : E->start_token[col];
-            else x = E->x_emb[(size_t)A.tokens[(size_t)b * A.tok_stride + t - 1] * W + col];
-            x += E->pos_emb[(size_t)t * W + col];
-            if (A.x_cond) x += A.x_cond[((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + col];
+    for (int e0 = c * kConsumers; e0 < B * W; e0 += G * kConsumers) {
+        const int e = e0 + tid;
+        const bool act = e < B * W;
+        const int b = act ? e / W : 0, col = act ? e - b * W : 0;
+        float hv = 0.f;
+        if (act) {
+            float x;
+            if (A.x_in) {
+                x = A.x_in[e];
+            } else {
+                if (t == 0) x = A.y_cond ? A.y_cond[e] : E->start_token[col];
+                else x = E->x_emb[(size_t)A.tokens[(size_t)b * A.tok_stride + t - 1] * W + col];
+                x += E->pos_emb[(size_t)t * W + col];
+                if (A.x_cond) x += A.x_cond[((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + col];
+            }
+            const __half hh = __float2half_rn(x);
+            E->h[e] = hh;
+            hv = __half2float(hh);
         }
-        E->h[e] = __float2half_rn(x);
+        // LayerNorm statistics of layer 0's input: warp-reduce when the warp sits in one row
+        long long s1 = act ? fx_sum(hv) : 0, s2 = act ? fx_sq(hv) : 0;
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        if (__all_sync(0xffffffffu, (!act) || b == b0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if ((tid & 31) == 0 && (s1 != 0 || s2 != 0)) {
+                red_add_s64(E->lnacc + 16 * (2 * b0), s1);
+                red_add_s64(E->lnacc + 16 * (2 * b0 + 1), s2);
+            }
+        } else if (act) {
+            red_add_s64(E->lnacc + 16 * (2 * b), s1);
+            red_add_s64(E->lnacc + 16 * (2 * b + 1), s2);
+        }
     }
     GRID_BARRIER();
 
+#pragma unroll 1
     for (int l = 0; l < E->depth; ++l) {
         const LayerDev& LD = E->layer[l];
         const ushort2* cl = E->cols + ((size_t)c * E->depth + l) * 4;
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
-        gemm_phase<true, EPI_QKV>(E, ring, uni, stats, E->h, W, Nqkv, cl[0].x, cl[0].y, B, LD.ln0_g, LD.ln0_b, LD.b_qkv);
+        GemmArgs ga;
+        ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
+        ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
+        ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
+        gemm_phase(E, ring, B, ga);
         GRID_BARRIER();
         {
             const AttnGeom geo = attn_geom(E, LD, t);
-            const int ns = attn_nsplit(E, LD, B, geo.R);
+            const int ns = attn_nsplit(E, B, geo.R - (geo.cur ? 1 : 0));
             for (int it = c; it < B * E->H * ns; it += G) {
                 const int s = it % ns, bh = it / ns;
-                attn_item(E, LD, uni, stats, bh / E->H, bh % E->H, s, ns, geo);
+                attn_item(E, LD, bh / E->H, bh % E->H, s, ns, geo, (int)nbar);
             }
             GRID_BARRIER();
-            if (ns > 1) {
-                for (int it = c; it < B * E->H; it += G) attn_merge(E, it / E->H, it % E->H, ns);
-                GRID_BARRIER();
-            }
         }
-        gemm_phase<false, EPI_PROJ>(E, ring, uni, stats, E->a, S, W, cl[1].x, cl[1].y, B, nullptr, nullptr, LD.b_o);
+        if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
+        ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
+        ga.pslot = (int)nbar; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
+        gemm_phase(E, ring, B, ga);
         GRID_BARRIER();
-        gemm_phase<true, EPI_FC>(E, ring, uni, stats, E->x1, W, M, cl[2].x, cl[2].y, B, LD.ln1_g, LD.ln1_b, LD.b_1);
+        ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
+        ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
+        ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
+        gemm_phase(E, ring, B, ga);
         GRID_BARRIER();
-        gemm_phase<false, EPI_PROJ2>(E, ring, uni, stats, E->g, M, W, cl[3].x, cl[3].y, B, nullptr, nullptr, LD.b_2);
+        if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l + 1) * 512 + 16 * tid] = 0;  // LN1 statistics are consumed
+        ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
+        ga.pslot = (int)nbar; ga.bias = LD.b_2; ga.ln_in = nullptr;
+        ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
+        gemm_phase(E, ring, B, ga);
         GRID_BARRIER();
     }
     if (A.h_out) {
         for (int e = c * kConsumers + tid; e < B * W; e += G * kConsumers)
             A.h_out[e] = ld_half_cg(E->h + e);
     }
-    if (do_logits) logits_phase(E, A, ring, uni, c, t);
+    if (do_logits) logits_phase(E, A, ring, c, t);
     if (c == 0 && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (nbar + 1 < (unsigned)kProfSlots) E->prof[nbar + 1] = now;
         *E->t = t + 1;
-        *E->epoch = epoch0 + nbar * (unsigned)G;
+        *E->epoch = epoch0 + nbar;
     }
 #undef GRID_BARRIER
 }
@@ -814,7 +1026,7 @@ struct jk_prior {
 namespace {
 
 struct Layout {
-    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_sync, total;
+    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_sync, total;
     size_t stream_stride;
     std::vector<ushort2> cols;
     std::vector<uint32_t> soff, goff;
@@ -896,7 +1108,8 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     size_t uni = (size_t)16 * (Kmax + 8) * 2;
     uni = std::max(uni, (size_t)16 * kLogitKT * 4);
     uni = std::max(uni, (size_t)8 * 8 * 16 * 8 * 4);                              // cross-warp reduction
-    size_t attn = (size_t)(3 + 8) * L.dh_pad * 4 + (size_t)std::max(c.n_ctx, std::max(c.encoder_dims, 1)) * 4;
+    const int TR = attn_tile_rows(L.dh_pad);
+    size_t attn = (size_t)4 * (TR + 1) * L.dh_pad * 2 + (size_t)(L.dh_pad + 4 * (TR + 1)) * 4 + 64;
     uni = std::max(uni, attn);
     L.uni_bytes = (int)align_up(uni, 1024);
     const int max_smem = 232448;
@@ -933,7 +1146,12 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     L.off_a = off;   off = align_up(off + (size_t)16 * c.n_state * 2, 256);
     L.off_g = off;   off = align_up(off + (size_t)16 * c.mlp_width * 2, 256);
     L.off_part = off; off = align_up(off + (size_t)c.max_batch * c.heads * kMaxSplit * (L.dh_pad + 2) * 4, 256);
-    L.off_sync = off; off += 256;
+    L.off_acnt = off; off = align_up(off + (size_t)c.max_batch * c.heads * 4, 256);
+    L.off_prof = off; off = align_up(off + (size_t)kProfSlots * 8, 256);
+    L.off_prof2 = off; off = align_up(off + (size_t)kProfSlots * 8 * 8, 256);
+    L.off_prof3 = off; off = align_up(off + (size_t)5 * 256 * 2 * 8, 256);
+    L.off_lnacc = off; off = align_up(off + (size_t)2 * depth * 512 * 8, 256);
+    L.off_sync = off; off += 8192;
     L.total = off;
     return 0;
 }
@@ -1000,7 +1218,16 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.streams = A + L.off_streams; E.stream_stride = L.stream_stride;
     E.h = (__half*)(A + L.off_h); E.x1 = (__half*)(A + L.off_x1); E.qkv = (__half*)(A + L.off_qkv);
     E.a = (__half*)(A + L.off_a); E.g = (__half*)(A + L.off_g); E.part = (float*)(A + L.off_part);
-    E.bar = (unsigned*)(A + L.off_sync); E.epoch = E.bar + 16; E.t = (int*)(E.bar + 32);
+    E.acnt = (unsigned*)(A + L.off_acnt); E.prof = (unsigned long long*)(A + L.off_prof);
+    E.lnacc = (long long*)(A + L.off_lnacc);
+    E.prof2 = (long long*)(A + L.off_prof2);
+    E.prof3 = (unsigned long long*)(A + L.off_prof3);
+    {
+        const char* sr = getenv("JK_ATTN_SPLIT_ROWS");
+        E.split_rows = sr ? atoi(sr) : 96;
+        if (E.split_rows < 8) E.split_rows = 8;
+    }
+    E.bar = (unsigned*)(A + L.off_sync); E.epoch = E.bar + 1536; E.t = (int*)(E.bar + 1568);
     size_t enc_off = L.off_small + L.small_per_layer * cfg->depth;
     for (int i = 0; i < 4; ++i) { p->bias_ptr[i].resize(cfg->depth); p->ln_ptr[i].resize(cfg->depth); }
     p->enc_w.assign(cfg->depth, nullptr); p->enc_b.assign(cfg->depth, nullptr);
@@ -1164,6 +1391,9 @@ extern "C" int jk_prior_debug_buffer(const jk_prior* p, int which, const void** 
         case 2: *ptr = p->host.a; *n = (size_t)16 * c.n_state; break;
         case 3: *ptr = p->host.x1; *n = (size_t)16 * c.width; break;
         case 4: *ptr = p->host.g; *n = (size_t)16 * c.mlp_width; break;
+        case 5: *ptr = p->host.prof; *n = (size_t)kProfSlots * 4; break;     /* uint64 timestamps */
+        case 7: *ptr = p->host.prof3; *n = (size_t)5 * 256 * 2 * 4; break;
+        case 6: *ptr = p->host.prof2; *n = (size_t)kProfSlots * 8 * 4; break; /* int64 clock64 stamps [slot][8] */
         default: JK_REQUIRE(false, "unknown buffer %d", which);
     }
     return 0;

@@ -20,6 +20,10 @@ class BottleneckBlock(nn.Module):
         x = x.float().contiguous()
         idx = t.empty(x.shape[0], dtype=t.int64, device=x.device)
         dist = t.empty(x.shape[0], dtype=t.float32, device=x.device)
+        if x.shape[0] == 0:
+            if not x.is_cuda:
+                raise RuntimeError("jukebox_b200 kernels need CUDA tensors (no CPU fallback)")
+            return idx, dist
         check(lib().jk_vq_argmin(ptr(x), ptr(self.k.float().contiguous()), ptr(idx), ptr(dist), x.shape[0],
                                  self.k_bins, self.emb_width, stream_ptr()))
         return idx, dist
@@ -27,6 +31,8 @@ class BottleneckBlock(nn.Module):
     def dequantise(self, x_l):
         x_l = x_l.contiguous().view(-1).long()
         out = t.empty(x_l.shape[0], self.emb_width, dtype=t.float32, device=x_l.device)
+        if x_l.shape[0] == 0:
+            return out
         check(lib().jk_vq_gather(ptr(x_l), ptr(self.k.float().contiguous()), ptr(out), x_l.shape[0], self.k_bins,
                                  self.emb_width, stream_ptr()))
         return out

@@ -165,7 +165,7 @@ TINY_PRIORS = {
     "sep_enc_dec": ("small_vqvae", dict(sample_length=64 * 256),
                     "small_sep_enc_dec_prior",
                     dict(n_ctx=64, prior_width=64, prior_depth=10, heads=2, blocks=4, n_tokens=16,
-                         prime_width=32, prime_depth=3, prime_heads=2, prime_blocks=4, level=1, levels=2,
+                         prime_width=64, prime_depth=3, prime_heads=2, prime_blocks=4, level=1, levels=2,
                          merged_decoder=True)),
 }
 

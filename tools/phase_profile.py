@@ -1,0 +1,90 @@
+"""Per-phase timing of the persistent decode kernel from its own globaltimer stamps (CTA 0).
+
+    python tools/phase_profile.py [--small] [--pos 4000]
+
+Prints the mean time between consecutive grid barriers, grouped by phase type, for a few tokens at
+the given position of the 1b_lyrics workload."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--pos", type=int, default=4000)
+    ap.add_argument("--n", type=int, default=16)
+    args = ap.parse_args()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        prior = bench.build_prior(args.small)
+    n = args.n
+    ca = prior.prior
+    eng = ca._engine(n)
+    L = ca.input_dims
+    toks = torch.randint(0, ca.bins, (n, L), device="cuda")
+    lbuf = torch.empty(n, ca.bins, device="cuda")
+    yc = torch.randn(n, ca.width, device="cuda")
+    xc = torch.zeros(n, 1, ca.width, device="cuda")
+    depth = ca.transformer.n_depth
+    funcs = [l.attn_func for l in ca.transformer._attn_mods]
+    pos = min(args.pos, L - 8)
+    eng.reset(pos)
+    rows = []
+    for i in range(6):
+        eng.step(n, tokens=toks, y_cond=yc, x_cond=xc, logits=lbuf)
+        torch.cuda.synchronize()
+        prof = eng.debug_buffer(5).view(torch.int64).cpu().numpy()
+        stamps = prof[: 2 + 5 * depth + 1].astype(np.float64)
+        if i >= 2:
+            rows.append(np.diff(stamps))
+    d = np.mean(rows, 0) / 1e3          # us
+    print(f"position {pos}, n={n}, depth={depth}: kernel total {d.sum():.1f} us")
+    print(f"  embed                : {d[0]:8.2f} us")
+    names = ["LN+QKV gemm", "attention", "proj gemm", "LN+FC gemm+gelu", "proj2 gemm"]
+    per = d[1:1 + 5 * depth].reshape(depth, 5)
+    for j, nm in enumerate(names):
+        print(f"  {nm:20s} : mean {per[:, j].mean():7.2f} us  min {per[:, j].min():7.2f}  max {per[:, j].max():7.2f}   (x{depth})")
+    for f in sorted(set(funcs)):
+        sel = [i for i, g in enumerate(funcs) if g == f]
+        print(f"     attention attn_func {f}: mean {per[sel, 1].mean():7.2f} us over {len(sel)} layers")
+    print(f"  logits + tail        : {d[1 + 5 * depth]:8.2f} us")
+    print(f"  per layer            : {per.sum(1).mean():8.2f} us")
+    # intra-phase stamps of CTA 0 (SM clock cycles): slot = index of the barrier that precedes the phase
+    p2 = eng.debug_buffer(6).view(torch.int64).cpu().numpy().reshape(-1, 8).astype(np.float64)
+    mhz = 1965.0
+    print("  CTA 0, GEMM phases (us): stage | mma+weights | reduce+epilogue | arrive->barrier-exit")
+    for j, nm in ((0, "LN+QKV"), (2, "proj"), (3, "LN+FC"), (4, "proj2")):
+        rows = []
+        for l in range(depth):
+            slot = 1 + 5 * l + j
+            s0, s1, s2, s3, s4, s5 = p2[slot, :6]
+            rows.append([(s1 - s0), (s2 - s1), (s3 - s2), (s5 - s4), p2[slot, 6]])
+        r = np.mean(rows, 0) / mhz
+        print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}   (of the mma time, waiting on the weight ring: {r[4]:5.2f} us)")
+    att = np.mean([(p2[1 + 5 * l + 1, 5] - p2[1 + 5 * l + 1, 4]) for l in range(depth)]) / mhz
+    attw = np.mean([(p2[1 + 5 * l + 1, 4] - p2[1 + 5 * l, 5]) for l in range(depth)]) / mhz
+    print(f"     attention (CTA 0): work {attw:6.2f} us, then waits {att:6.2f} us in the barrier")
+    ar = np.array([[p2[1 + 5 * l + 1, i] for i in (0, 1, 2, 3, 6, 4)] for l in range(depth) if funcs[l] in (1, 3)]) / mhz
+    d_ = np.diff(ar, axis=1).mean(0)
+    print(f"     attention block/prev layers, CTA 0 (us): load+sync {d_[0]:5.2f} | scores {d_[1]:5.2f} | softmax+PV {d_[2]:5.2f} | publish+merge {d_[3]:5.2f} | to barrier {d_[4]:5.2f}")
+    p3 = eng.debug_buffer(7).view(torch.int64).cpu().numpy().reshape(5, 256, 2).astype(np.float64)
+    G = torch.cuda.get_device_properties(0).multi_processor_count
+    print("  layer 1, all CTAs (globaltimer, us): arrival spread min/median/max after the first arrival; exit - last arrival")
+    for j, nm in enumerate(["LN+QKV", "attention", "proj", "LN+FC", "proj2"]):
+        arr, ex = p3[j, :G, 0], p3[j, :G, 1]
+        a0 = arr.min()
+        order = np.argsort(arr)
+        print(f"     {nm:10s}: arrivals {0:5.2f} / {np.median(arr - a0) / 1e3:5.2f} / {(arr.max() - a0) / 1e3:5.2f}   "
+              f"exit-last_arrival {np.median(ex - arr.max()) / 1e3:5.2f}   slowest CTAs {order[-4:].tolist()} fastest {order[:3].tolist()}")
+
+
+if __name__ == "__main__":
+    main()
