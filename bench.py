@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-tokens", type=int, default=24, help="tokens per sample in the CPU baseline sample")
     ap.add_argument("--small", action="store_true", help="tiny debug configuration (not a valid bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="prior", choices=["prior", "vqvae_decode"],
+                    help="prior = BASELINE configs[1] (default, the bench line); vqvae_decode = configs[4] secondary metric")
     return ap.parse_args()
 
 
@@ -261,6 +263,86 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------
+def run_vqvae(args, rank, world, local):
+    """BASELINE configs[4]: 3-level VQ-VAE decode, sample_length 1048576, bs 16 per GPU; one step = every
+    clip decoded at every level exactly as sample.py:108 does (decode(zs[l:], start_level=l, bs_chunks=N))."""
+    import contextlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from jukebox_b200.hparams import setup_hparams
+    from jukebox_b200.make_models import make_vqvae
+    T = 1048576 if not args.small else 65536
+    n = N_SAMPLES if not args.small else 2
+    with contextlib.redirect_stdout(sys.stderr), torch.device("cuda"):
+        vq = make_vqvae(setup_hparams("vqvae", dict(sample_length=T, restore_vqvae="")), "cuda")
+    synth_fill(vq, 5)
+    for blk in vq.bottleneck.level_blocks:
+        blk.k.normal_()
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    zs_host = [torch.randint(0, vq.l_bins, (n, T // int(h)), generator=g, device="cuda").cpu().pin_memory()
+               for h in vq.hop_lengths]
+
+    def step(zs):
+        outs = [vq.decode(zs[l:], start_level=l, bs_chunks=n) for l in range(vq.levels)]
+        return outs
+
+    zs_dev = [z.cuda() for z in zs_host]
+    for _ in range(max(args.warmup, 1)):
+        step(zs_dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0.record()
+    for _ in range(args.steps):
+        step(zs_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outs = step([z.cuda(non_blocking=True) for z in zs_host])
+        x_host = outs[0][:1].cpu()           # audio of the finest level, first clip (result read-back)
+    torch.cuda.synchronize()
+    wall = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    from jukebox_b200 import _lib
+    c0 = _lib.CALLS
+    step(zs_dev)
+    launches_per_step = _lib.CALLS - c0
+    if rank != 0:
+        return
+    clips = world * n * args.steps
+    value = clips / (float(ms) * 1e-3)
+    flops_clip = 373e9 * (T / 1048576)
+    bytes_plan = 7.3e9 * (T / 1048576)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    t_clip = float(ms) * 1e-3 / (n * args.steps)
+    line = dict(metric="vqvae_decode_clips_per_sec", value=value, unit="clips/s (3 levels each)", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=float(ms) / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="vqvae_3level_decode_sample_length%d_bs%d" % (T, n), l2_policy="activations (268 MB per conv at level 0) exceed L2"),
+                e2e=dict(value=clips / float(wall), unit="clips/s", h2d_bytes_per_step=int(sum(z.numel() for z in zs_host) * 8),
+                         d2h_bytes_per_step=int(x_host.numel() * 4), api="VQVAE.decode(zs[l:], start_level=l, bs_chunks=N) for l in 0..2"),
+                gpu_launches=int(launches_per_step * args.steps),
+                roofline=dict(bound="hbm", achieved=bytes_plan / t_clip / 1e9, peak=hbm, unit="GB/s",
+                              frac=bytes_plan / t_clip / 1e9 / hbm, traffic=None, kernel="conv1d_cl_kernel",
+                              note="per-block-fused activation plan 7.3 GB fp32 per clip (SURVEY 8d); compute side: %.1f TFLOP/s fp32 achieved" % (flops_clip / t_clip / 1e12)),
+                clocks=clocks)
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -280,7 +362,14 @@ def main():
 
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):      # model-construction chatter must not precede the JSON line
-        prior = build_prior(args.small, seed=rank)
+        from jukebox_b200.utils.dist_sampling import scatter_rows, gather_rows, seed_per_rank
+    seed_per_rank(0)
+    if args.workload == "vqvae_decode":
+        run_vqvae(args, rank, world, local)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    prior = build_prior(args.small, seed=rank)
     n = N_SAMPLES
     tokens_per_window = n * prior.n_ctx
     sample_kw = dict(fp16=True, temp=0.99, chunk_size=32)
@@ -296,18 +385,9 @@ def main():
 
     def window_e2e():
         """public API with host buffers: labels H2D (+ NCCL scatter), sample, codes D2H (+ gather)"""
-        if world > 1:
-            y_all = y_all_host.cuda(non_blocking=True) if rank == 0 else torch.empty_like(y_all_host, device="cuda")
-            dist.broadcast(y_all, 0)
-            y = y_all[rank * n:(rank + 1) * n].contiguous()
-        else:
-            y = y_all_host.cuda(non_blocking=True)
+        y = scatter_rows(y_all_host, n, torch.device("cuda", local))
         z = prior.sample(n_samples=n, z=None, z_conds=None, y=y, **sample_kw)
-        if world > 1:
-            out = [torch.empty_like(z) for _ in range(world)] if rank == 0 else None
-            dist.gather(z, out, 0)
-            z = torch.cat(out) if rank == 0 else z
-        return z.cpu()
+        return gather_rows(z).cpu()
 
     y_dev = y_all_host[rank * n:(rank + 1) * n].cuda()
     with torch.no_grad():

@@ -90,7 +90,12 @@ def lib():
     return _lib
 
 
+CALLS = 0      # C-ABI calls that enqueue GPU work (bench.py reports it as its launch evidence)
+
+
 def check(rc):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise RuntimeError("libjkb200: " + lib().jk_last_error().decode())
 

@@ -44,7 +44,7 @@ constexpr int kConsumers = 256;
 constexpr int kThreads = 288;          // 8 consumer warps + 1 producer warp
 constexpr int kSlotBytes = 16384;
 constexpr int kMaxSlots = 12;
-constexpr int kHeaderBytes = 1024;     // barriers + LN statistics
+constexpr int kHeaderBytes = 2048;     // barriers, LN statistics, shared copies of the descriptor / layer records
 constexpr int kLogitKT = 1024;         // K tile (floats) of the fp32 logits product
 constexpr int kLogitRowsPerChunk = 4;
 constexpr int kLogitRowsPerPass = 8;
@@ -65,7 +65,7 @@ struct LayerDev {
 
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes;
+    int nslot, uni_bytes, kvpre_bytes;
     float scale2;
     const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
     const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
@@ -110,6 +110,14 @@ __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64
 __device__ __forceinline__ float* sm_stats() { return reinterpret_cast<float*>(jk_smem + 256); }
 __device__ __forceinline__ long long* sm_sacc() { return reinterpret_cast<long long*>(jk_smem + 512); }
 __device__ __forceinline__ uint8_t* sm_uni() { return jk_smem + kHeaderBytes; }
+struct EngineDev;
+struct LayerDev;
+// The engine descriptor lives in global memory; with the shared-memory carve-out at its maximum there is
+// no L1 to cache it, so every `E->field` was an L2 round trip (~300 cycles) on the dependency chain.
+// The head of the descriptor (everything before the per-layer array) and the current / next layer
+// records are therefore copied into shared memory once and read with LDS.
+__device__ __forceinline__ const EngineDev* sm_E() { return reinterpret_cast<const EngineDev*>(jk_smem + 512); }
+__device__ __forceinline__ const LayerDev* sm_layer(int i) { return reinterpret_cast<const LayerDev*>(jk_smem + 1024 + 256 * (i & 1)); }
 
 struct Ring {
     int base_off;          // byte offset of slot 0 inside jk_smem
@@ -287,7 +295,8 @@ struct GemmArgs {
     long long* ln_out;
 };
 
-__device__ __noinline__ void gemm_phase(const EngineDev* E, Ring& ring_ref, int B, const GemmArgs& g_ref) {
+__device__ __noinline__ void gemm_phase(Ring& ring_ref, int B, const GemmArgs& g_ref) {
+    const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     if (g_ref.ncg == 0) return;
     const GemmArgs g = g_ref;              // by value: keeps the arguments and the ring cursor in registers
@@ -452,9 +461,11 @@ __device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache
 //   * softmax is flash-style in fp32 (running max / sum, unnormalised P), P.V by one thread per
 //     output dimension; parts of one (sample, head) are merged by the last CTA to finish (atomic
 //     ticket), so the phase needs no extra grid barrier
-__device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_ref, int b, int h, int s, int ns,
-                                       const AttnGeom& G_ref, int pslot) {
+__device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int s, int ns,
+                                       const AttnGeom& G_ref, int pslot, int pre) {
+    const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
+    uint8_t* tiles = pre ? (jk_smem + kHeaderBytes + E->uni_bytes) : uni;   // K/V tile buffers
     float* stats = sm_stats();
     const LayerDev LD = LD_ref;
     const AttnGeom G = G_ref;
@@ -494,7 +505,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
 
     auto issue_tile = [&](int ti) {
         const int r0 = i0 + ti * trows, nr = max(0, min(trows, i1 - r0));
-        const uint32_t kd = smem_u32(uni + (one_shot ? 0 : (ti & 1) * 2 * tileB)), vd = kd + voff;
+        const uint32_t kd = smem_u32(tiles + (one_shot ? 0 : (ti & 1) * 2 * tileB)), vd = kd + voff;
         const __half* ks = kbase + (size_t)r0 * dhp;
         const __half* vs = vbase + (size_t)r0 * dhp;
 #pragma unroll 2
@@ -504,7 +515,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue_tile(0);
+    if (!pre) issue_tile(0);
     for (int d = tid; d < dhp; d += kConsumers) qs[d] = (d < dh) ? ld_half_cg(qrow + d) : 0.f;
     if (!G.cur && G.wrow >= 0 && last_part) {   // patterns that do not attend the current token still cache it
         for (int d = tid; d < dh; d += kConsumers) {
@@ -529,7 +540,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
         }
         const int r0 = i0 + ti * trows;
         int nr = max(0, min(trows, i1 - r0));
-        __half* kt = reinterpret_cast<__half*>(uni + (one_shot ? 0 : (ti & 1) * 2 * tileB));
+        __half* kt = reinterpret_cast<__half*>(tiles + (one_shot ? 0 : (ti & 1) * 2 * tileB));
         __half* vt = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(kt) + voff);
         if (ti == ntiles - 1 && last_part && G.cur) {       // append the current token's k, v (from the QKV GEMM)
             for (int d = tid; d < dhp; d += kConsumers) {
@@ -555,7 +566,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
             const int r = base + rr;
             float dot = 0.f;
             if (r < nr) {
-#pragma unroll 1
+#pragma unroll 4
                 for (int v = sl; v < nvec; v += SL) {
                     const uint4 q4 = *reinterpret_cast<const uint4*>(kt + r * dhp + v * 8);
                     const __half2* hp = reinterpret_cast<const __half2*>(&q4);
@@ -574,7 +585,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
         STAMP(E, pslot, 2);
         if (nr > 0) {
             float m_t = -INFINITY;
-#pragma unroll 1
+#pragma unroll 8
             for (int r = 0; r < nr; ++r) m_t = fmaxf(m_t, sc[r]);
             const float m_new = fmaxf(m_run, m_t);
             const float corr = expf(m_run - m_new);          // exp(-inf) = 0 on the first tile
@@ -584,7 +595,7 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
             float lt = 0.f, a0 = acc[0] * corr, a1 = acc[1] * corr;
             const bool d1 = tid + kConsumers < dhp;
             if (tid < dhp) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int r = 0; r < nr; ++r) {
                     const float pr = sp[r];
                     lt += pr;
@@ -645,6 +656,36 @@ __device__ __noinline__ void attn_item(const EngineDev* E, const LayerDev& LD_re
     STAMP(E, pslot, 6);
 }
 
+// Prefetch of the cached K/V rows of this CTA's first attention work item, issued BEFORE the QKV GEMM of
+// the layer: cached rows do not depend on the current token, so their HBM latency hides behind the
+// whole QKV phase and its barrier.  Only single-tile ("one shot") parts are prefetched; returns 1 if so.
+__device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t) {
+    const EngineDev* E = sm_E();
+    if (E->kvpre_bytes == 0) return 0;
+    const LayerDev LD = LD_ref;
+    const AttnGeom G = attn_geom(E, LD, t);
+    if (G.R == 0) return 0;
+    const int ncache = G.R - (G.cur ? 1 : 0);
+    const int ns = attn_nsplit(E, B, ncache);
+    if (c >= B * E->H * ns) return 0;
+    const int s = c % ns, bh = c / ns, b = bh / E->H, h = bh % E->H;
+    const int dhp = E->dh_pad, nvec = dhp >> 3, TR = attn_tile_rows(dhp);
+    const int tileB = (TR + 1) * dhp * 2;
+    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
+    if (i1 - i0 > 2 * TR) return 0;
+    const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
+    const __half* ks = LD.kc + (cbase + G.base + i0) * dhp;
+    const __half* vs = LD.vc + (cbase + G.base + i0) * dhp;
+    const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + 2 * tileB;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < (i1 - i0) * nvec; i += kConsumers) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + i * 16), "l"(ks + i * 8));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + i * 16), "l"(vs + i * 8));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return 1;
+}
+
 // ---------------------------------------------------------------------------------------
 // producer warp: walks this CTA's weight stream (and the logits rows) in consumption order
 // ---------------------------------------------------------------------------------------
@@ -693,7 +734,8 @@ __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool d
 
 // fp32 logits: logits[b, r] = sum_k y[b, k] * x_out[r, k],  y = float(h) (+ cond)
 // (reference autoregressive.py:226-229: fp32 nn.Linear on the fp32 transformer output)
-__device__ __noinline__ void logits_phase(const EngineDev* E, const StepArgs& A_ref, Ring& ring_ref, int c, int t) {
+__device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref, int c, int t) {
+    const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     const StepArgs A = A_ref;
     Ring ring = ring_ref;
@@ -781,11 +823,19 @@ __device__ __noinline__ void logits_phase(const EngineDev* E, const StepArgs& A_
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const EngineDev* __restrict__ E, StepArgs A) {
+__global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const EngineDev* __restrict__ Eg, StepArgs A) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int c = blockIdx.x;
+    static_assert(offsetof(EngineDev, layer) <= 512, "descriptor head must fit its shared-memory slot");
+    static_assert(sizeof(LayerDev) <= 256, "layer record must fit its shared-memory slot");
+    for (int i = tid; i < (int)(offsetof(EngineDev, layer) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(jk_smem + 512)[i] = reinterpret_cast<const uint32_t*>(Eg)[i];
+    if (tid < (int)(sizeof(LayerDev) / 4))
+        reinterpret_cast<uint32_t*>(jk_smem + 1024)[tid] = reinterpret_cast<const uint32_t*>(&Eg->layer[0])[tid];
+    __syncthreads();
+    const EngineDev* E = sm_E();
     Ring ring;
-    ring.base_off = kHeaderBytes + E->uni_bytes; ring.nslot = E->nslot; ring.slot = 0; ring.phase = 0;
+    ring.base_off = kHeaderBytes + E->uni_bytes + E->kvpre_bytes; ring.nslot = E->nslot; ring.slot = 0; ring.phase = 0;
     if (tid == 0) {
         for (int i = 0; i < E->nslot; ++i) { mbar_init(sm_full() + i, 1); mbar_init(sm_empty() + i, 8); }
         mbar_fence_init();
@@ -793,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     __syncthreads();
     const bool do_logits = (A.logits != nullptr) && E->bins > 0;
     if (warp == 8) {
-        producer_loop(E, ring, do_logits, c);
+        producer_loop(Eg, ring, do_logits, c);
         return;
     }
     const int t = *reinterpret_cast<volatile const int*>(E->t);
@@ -870,46 +920,50 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
 
 #pragma unroll 1
     for (int l = 0; l < E->depth; ++l) {
-        const LayerDev& LD = E->layer[l];
+        const LayerDev& LD = *sm_layer(l);
         const ushort2* cl = E->cols + ((size_t)c * E->depth + l) * 4;
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
+        const int pre_ok = attn_prefetch(LD, B, c, t);
         GemmArgs ga;
         ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
         ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
         ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
-        gemm_phase(E, ring, B, ga);
+        gemm_phase(ring, B, ga);
         GRID_BARRIER();
+        if (l + 1 < E->depth && tid < (int)(sizeof(LayerDev) / 4))      // next layer's record -> the other slot
+            reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1))[tid] =
+                reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1])[tid];
         {
             const AttnGeom geo = attn_geom(E, LD, t);
             const int ns = attn_nsplit(E, B, geo.R - (geo.cur ? 1 : 0));
             for (int it = c; it < B * E->H * ns; it += G) {
                 const int s = it % ns, bh = it / ns;
-                attn_item(E, LD, bh / E->H, bh % E->H, s, ns, geo, (int)nbar);
+                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nbar, pre_ok && it == c);
             }
             GRID_BARRIER();
         }
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
         ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
         ga.pslot = (int)nbar; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
-        gemm_phase(E, ring, B, ga);
+        gemm_phase(ring, B, ga);
         GRID_BARRIER();
         ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
         ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
         ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
-        gemm_phase(E, ring, B, ga);
+        gemm_phase(ring, B, ga);
         GRID_BARRIER();
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l + 1) * 512 + 16 * tid] = 0;  // LN1 statistics are consumed
         ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
         ga.pslot = (int)nbar; ga.bias = LD.b_2; ga.ln_in = nullptr;
         ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
-        gemm_phase(E, ring, B, ga);
+        gemm_phase(ring, B, ga);
         GRID_BARRIER();
     }
     if (A.h_out) {
         for (int e = c * kConsumers + tid; e < B * W; e += G * kConsumers)
             A.h_out[e] = ld_half_cg(E->h + e);
     }
-    if (do_logits) logits_phase(E, A, ring, c, t);
+    if (do_logits) logits_phase(A, ring, c, t);
     if (c == 0 && tid == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1035,7 +1089,7 @@ struct Layout {
     std::vector<size_t> cache_bytes;
     std::vector<int> cache_rows;
     size_t small_per_layer;
-    int dh, dh_pad, bc, prime_pad, uni_bytes, nslot, smem_bytes;
+    int dh, dh_pad, bc, prime_pad, uni_bytes, kvpre_bytes, nslot, smem_bytes;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1113,11 +1167,13 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     uni = std::max(uni, attn);
     L.uni_bytes = (int)align_up(uni, 1024);
     const int max_smem = 232448;
-    int nslot = (max_smem - kHeaderBytes - L.uni_bytes) / kSlotBytes;
+    L.kvpre_bytes = (int)align_up((size_t)4 * (TR + 1) * L.dh_pad * 2, 1024);
+    if (getenv("JK_NO_KV_PREFETCH") || (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes < 4) L.kvpre_bytes = 0;
+    int nslot = (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes;
     nslot = std::min(nslot, kMaxSlots);
     JK_REQUIRE(nslot >= 2, "not enough shared memory for the weight ring (uni %d bytes)", L.uni_bytes);
     L.nslot = nslot;
-    L.smem_bytes = kHeaderBytes + L.uni_bytes + nslot * kSlotBytes;
+    L.smem_bytes = kHeaderBytes + L.uni_bytes + L.kvpre_bytes + nslot * kSlotBytes;
 
     size_t off = 0;
     L.off_dev = off; off = align_up(off + sizeof(EngineDev), 256);
@@ -1205,7 +1261,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes;
+    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);
