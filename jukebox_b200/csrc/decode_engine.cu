@@ -65,7 +65,7 @@ struct LayerDev {
 
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes, kvpre_bytes;
+    int nslot, uni_bytes, kvpre_bytes, small_bytes;
     float scale2;
     const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
     const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
@@ -211,8 +211,8 @@ __device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
             const double m = (double)__ldcg(lnacc + 16 * (2 * tid)) * (1.0 / 16777216.0) * rk;
             double var = (double)__ldcg(lnacc + 16 * (2 * tid + 1)) * (1.0 / 65536.0) * rk - m * m;
             var = var < 0.0 ? 0.0 : var;
-            mean = (float)m;
             rstd = 1.0f / sqrtf((float)var + 1e-5f);
+            mean = -(float)m * rstd;                        // staged as x * rstd + (-mean * rstd), then * gamma + beta
         }
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rstd;
@@ -240,12 +240,12 @@ __device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     __half2* hp = reinterpret_cast<__half2*>(&x[r]);
-                    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+                    const float rstd = stats[2 * r + 1], nmr = stats[2 * r];     // nmr = -mean * rstd
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float2 f = __half22float2(hp[e]);
-                        f.x = (f.x - mean) * rstd * gm[2 * e] + bt[2 * e];
-                        f.y = (f.y - mean) * rstd * gm[2 * e + 1] + bt[2 * e + 1];
+                        f.x = fmaf(fmaf(f.x, rstd, nmr), gm[2 * e], bt[2 * e]);
+                        f.y = fmaf(fmaf(f.y, rstd, nmr), gm[2 * e + 1], bt[2 * e + 1]);
                         hp[e] = __floats2half2_rn(f.x, f.y);
                     }
                 }
@@ -295,12 +295,10 @@ struct GemmArgs {
     long long* ln_out;
 };
 
-__device__ __noinline__ void gemm_phase(Ring& ring_ref, int B, const GemmArgs& g_ref) {
+__device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
-    if (g_ref.ncg == 0) return;
-    const GemmArgs g = g_ref;              // by value: keeps the arguments and the ring cursor in registers
-    Ring ring = ring_ref;                  // (through the reference they live in local memory = L2 round trips)
+    if (g.ncg == 0) return ring;
     const int ncg = g.ncg;
     STAMP(E, g.pslot, 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -328,30 +326,27 @@ __device__ __noinline__ void gemm_phase(Ring& ring_ref, int B, const GemmArgs& g
     const int kpc = kpc_of(ncg);
     const int astride = (K + 8) * 2;
     const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
-    long long twait = 0;
-#pragma unroll 1
-    for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {
-        const int nk = min(kpc, nkk - kk0);
-        const long long tw0 = clock64();
-        mbar_wait(ring.full(), ring.phase);
-        twait += clock64() - tw0;
-        const uint32_t sl = smem_u32(ring.data()) + lane * 8;
-        switch (ncg) {
-            case 1: mma_chunk<1>(acc, arow, sl, kk0, nk, warp); break;
-            case 2: mma_chunk<2>(acc, arow, sl, kk0, nk, warp); break;
-            case 3: mma_chunk<3>(acc, arow, sl, kk0, nk, warp); break;
-            case 4: mma_chunk<4>(acc, arow, sl, kk0, nk, warp); break;
-            case 5: mma_chunk<5>(acc, arow, sl, kk0, nk, warp); break;
-            case 6: mma_chunk<6>(acc, arow, sl, kk0, nk, warp); break;
-            case 7: mma_chunk<7>(acc, arow, sl, kk0, nk, warp); break;
-            default: mma_chunk<8>(acc, arow, sl, kk0, nk, warp); break;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ring.empty());
-        ring.advance();
+#define JK_MMA_LOOP(NCG)                                                                      \
+    _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                            \
+        const int nk = min(kpc, nkk - kk0);                                                    \
+        mbar_wait(ring.full(), ring.phase);                                                    \
+        mma_chunk<NCG>(acc, arow, smem_u32(ring.data()) + lane * 8, kk0, nk, warp);            \
+        __syncwarp();                                                                          \
+        if (lane == 0) mbar_arrive(ring.empty());                                              \
+        ring.advance();                                                                        \
     }
+    switch (ncg) {
+        case 1: { JK_MMA_LOOP(1) } break;
+        case 2: { JK_MMA_LOOP(2) } break;
+        case 3: { JK_MMA_LOOP(3) } break;
+        case 4: { JK_MMA_LOOP(4) } break;
+        case 5: { JK_MMA_LOOP(5) } break;
+        case 6: { JK_MMA_LOOP(6) } break;
+        case 7: { JK_MMA_LOOP(7) } break;
+        default: { JK_MMA_LOOP(8) } break;
+    }
+#undef JK_MMA_LOOP
     STAMP(E, g.pslot, 2);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && g.pslot < kProfSlots) E->prof2[(size_t)g.pslot * 8 + 6] = twait;
     consumer_sync();                       // everyone is done reading the staged activations
     float* red = reinterpret_cast<float*>(uni);   // [8 warps][ncg][16][8]  (<= 32 KB)
     float* ov = reinterpret_cast<float*>(uni + 32768);   // [16][64] residual-stream outputs of this CTA
@@ -406,7 +401,7 @@ __device__ __noinline__ void gemm_phase(Ring& ring_ref, int B, const GemmArgs& g
         }
         consumer_sync();                   // ov is reused
     }
-    ring_ref = ring;
+    return ring;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -462,13 +457,12 @@ __device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache
 //     output dimension; parts of one (sample, head) are merged by the last CTA to finish (atomic
 //     ticket), so the phase needs no extra grid barrier
 __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int s, int ns,
-                                       const AttnGeom& G_ref, int pslot, int pre) {
+                                       const AttnGeom G, int pslot, int pre) {
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     uint8_t* tiles = pre ? (jk_smem + kHeaderBytes + E->uni_bytes) : uni;   // K/V tile buffers
     float* stats = sm_stats();
     const LayerDev LD = LD_ref;
-    const AttnGeom G = G_ref;
     const int tid = threadIdx.x, lane = tid & 31;
     const int dh = E->dh, dhp = E->dh_pad, S = E->S;
     const int nvec = dhp >> 3;
@@ -695,6 +689,13 @@ __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool d
     for (int l = 0; l < E->depth; ++l) {
         const ushort2* cl = E->cols + ((size_t)c * E->depth + l) * 4;
         const int Ks[4] = {E->W, E->S, E->W, E->M};
+        if (c == (l % E->G)) {
+            // biases + LayerNorm parameters of this layer (one contiguous block, ~57 KB for 1b_lyrics) are
+            // shared by every CTA and evicted from L2 between steps: pull them into L2 ahead of the consumers
+            // (this producer runs about a layer ahead of them)
+            const char* p0 = reinterpret_cast<const char*>(E->layer[l].b_qkv);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"((uint32_t)E->small_bytes) : "memory");
+        }
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
             const int ncg = cl[gi].y;
@@ -832,6 +833,9 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         reinterpret_cast<uint32_t*>(jk_smem + 512)[i] = reinterpret_cast<const uint32_t*>(Eg)[i];
     if (tid < (int)(sizeof(LayerDev) / 4))
         reinterpret_cast<uint32_t*>(jk_smem + 1024)[tid] = reinterpret_cast<const uint32_t*>(&Eg->layer[0])[tid];
+    if (tid >= 32 && tid < 36)
+        reinterpret_cast<uint32_t*>(jk_smem + 1024 + 128)[tid - 32] =
+            reinterpret_cast<const uint32_t*>(Eg->cols + ((size_t)c * Eg->depth + 0) * 4)[tid - 32];
     __syncthreads();
     const EngineDev* E = sm_E();
     Ring ring;
@@ -921,18 +925,26 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
 #pragma unroll 1
     for (int l = 0; l < E->depth; ++l) {
         const LayerDev& LD = *sm_layer(l);
-        const ushort2* cl = E->cols + ((size_t)c * E->depth + l) * 4;
+        const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
         const int pre_ok = attn_prefetch(LD, B, c, t);
         GemmArgs ga;
         ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
         ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
         ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
-        gemm_phase(ring, B, ga);
+        ring = gemm_phase(ring, B, ga);
+        // next layer's record + column assignment -> the other shared-memory slot.  The descriptor is in
+        // HBM (the weight stream evicts it from L2 every step): issue the loads here so their latency hides
+        // behind the barrier instead of sitting on the dependency chain.
+        if (l + 1 < E->depth) {
+            if (tid < (int)(sizeof(LayerDev) / 4))
+                reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1))[tid] =
+                    reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1])[tid];
+            if (tid >= 32 && tid < 36)
+                reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1) + 128)[tid - 32] =
+                    reinterpret_cast<const uint32_t*>(E->cols + ((size_t)c * E->depth + l + 1) * 4)[tid - 32];
+        }
         GRID_BARRIER();
-        if (l + 1 < E->depth && tid < (int)(sizeof(LayerDev) / 4))      // next layer's record -> the other slot
-            reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1))[tid] =
-                reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1])[tid];
         {
             const AttnGeom geo = attn_geom(E, LD, t);
             const int ns = attn_nsplit(E, B, geo.R - (geo.cur ? 1 : 0));
@@ -945,18 +957,18 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
         ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
         ga.pslot = (int)nbar; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
-        gemm_phase(ring, B, ga);
+        ring = gemm_phase(ring, B, ga);
         GRID_BARRIER();
         ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
         ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
         ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
-        gemm_phase(ring, B, ga);
+        ring = gemm_phase(ring, B, ga);
         GRID_BARRIER();
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l + 1) * 512 + 16 * tid] = 0;  // LN1 statistics are consumed
         ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
         ga.pslot = (int)nbar; ga.bias = LD.b_2; ga.ln_in = nullptr;
         ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
-        gemm_phase(ring, B, ga);
+        ring = gemm_phase(ring, B, ga);
         GRID_BARRIER();
     }
     if (A.h_out) {
@@ -1261,7 +1273,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes;
+    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);
