@@ -125,6 +125,13 @@ int jk_prior_position(const jk_prior* p, int* t);
  * which: 0 = h, 1 = qkv, 2 = attention out, 3 = x1 (x + a), 4 = gelu out.  Returns device ptr. */
 int jk_prior_debug_buffer(const jk_prior* p, int which, const void** ptr, size_t* n_halfs);
 
+/* Conv1D at prefill / training shape on the tensor cores (tcgen05 + TMA): y[M, N] = x[M, K] . w + b, fp16 in,
+ * fp32 accumulate, fp16 out (transformer/ops.py:83-101).  w_t is the weight TRANSPOSED: [N, K] row-major fp16;
+ * bias fp32 [N] or NULL; K must be a multiple of 64.  Used for c_enc_kv(encoder_kv)
+ * (factored_attention.py:273-287) inside jk_prior_set_encoder_kv. */
+int jk_conv1d_prefill_f16(const void* x, const void* w_t, const float* bias, void* y, int M, int N, int K,
+                          jk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * VQ-VAE.  Tensors are channels-last: [N, T, C] fp32.
  * ---------------------------------------------------------------------------------------- */

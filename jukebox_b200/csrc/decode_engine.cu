@@ -65,7 +65,7 @@ struct LayerDev {
 
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes, kvpre_bytes, small_bytes;
+    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on;
     float scale2;
     const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
     const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
@@ -134,7 +134,7 @@ struct Ring {
 
 #define STAMP(E_, slot_, i_)                                                                \
     do {                                                                                    \
-        if (blockIdx.x == 0 && threadIdx.x == 0 && (slot_) < kProfSlots)                     \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (E_)->prof_on && (slot_) < kProfSlots)      \
             (E_)->prof2[(size_t)(slot_) * 8 + (i_)] = clock64();                             \
     } while (0)
 
@@ -857,26 +857,26 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
 #define GRID_BARRIER()                                                                     \
     do {                                                                                   \
         STAMP(E, (int)nbar, 4);                                                            \
-        if (tid == 0 && nbar >= 6 && nbar < 11) {                                          \
+        if (tid == 0 && E->prof_on && nbar >= 6 && nbar < 11) {                            \
             unsigned long long now_;                                                       \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
             E->prof3[((nbar - 6) * 256 + c) * 2] = now_;                                   \
         }                                                                                  \
         ++nbar;                                                                            \
         grid_barrier(E->bar, epoch0 + nbar, c, G);                                         \
-        if (tid == 0 && nbar >= 7 && nbar < 12) {                                          \
+        if (tid == 0 && E->prof_on && nbar >= 7 && nbar < 12) {                            \
             unsigned long long now_;                                                       \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
             E->prof3[((nbar - 7) * 256 + c) * 2 + 1] = now_;                               \
         }                                                                                  \
         STAMP(E, (int)nbar - 1, 5);                                                        \
-        if (c == 0 && tid == 0 && nbar < (unsigned)kProfSlots) {                           \
+        if (c == 0 && tid == 0 && E->prof_on && nbar < (unsigned)kProfSlots) {             \
             unsigned long long now;                                                        \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));                        \
             E->prof[nbar] = now;                                                           \
         }                                                                                  \
     } while (0)
-    if (c == 0 && tid == 0) {
+    if (c == 0 && tid == 0 && E->prof_on) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         E->prof[0] = now;
@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     if (c == 0 && tid == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (nbar + 1 < (unsigned)kProfSlots) E->prof[nbar + 1] = now;
+        if (E->prof_on && nbar + 1 < (unsigned)kProfSlots) E->prof[nbar + 1] = now;
         *E->t = t + 1;
         *E->epoch = epoch0 + nbar;
     }
@@ -1034,34 +1034,35 @@ __global__ void to_half_kernel(const T* __restrict__ src, __half* dst, size_t n)
     if (i < n) dst[i] = to_half<T>(src[i]);
 }
 
-// encoder K/V for attn_func 6: kv[b, e, :] = fp16(enc[b, e, :] . Wkv + b)   (once per window)
-// simple tiled fp16 GEMM with fp32 accumulation; M = n*enc_dims rows.
-__global__ void enc_kv_kernel(const float* __restrict__ enc, const __half* __restrict__ w, const float* __restrict__ bias,
-                              __half* kc, __half* vc, int rows_total, int E_dims, int W, int S, int H, int dh, int dhp) {
-    __shared__ float xs[16][33];
-    __shared__ float ws[32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 16
-    const int row0 = blockIdx.y * 16, col0 = blockIdx.x * 32;
-    float acc = 0.f;
-    for (int k0 = 0; k0 < W; k0 += 32) {
-        int r = row0 + ty;
-        xs[ty][tx] = (r < rows_total && k0 + tx < W) ? __half2float(__float2half_rn(enc[(size_t)r * W + k0 + tx])) : 0.f;
-        for (int kk = ty; kk < 32; kk += 16)
-            ws[kk][tx] = (k0 + kk < W && col0 + tx < 2 * S) ? __half2float(w[(size_t)(k0 + kk) * 2 * S + col0 + tx]) : 0.f;
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) acc += xs[ty][kk] * ws[kk][tx];
-        __syncthreads();
+// encoder K/V for attn_func 6: kv = fp16(fp16(enc) . Wkv + b), once per window.  The product itself runs on
+// the tcgen05 prefill GEMM (prefill_gemm.cu); these kernels only convert / lay out its operands and result.
+template <typename T>
+__global__ void transpose_to_half_kernel(const T* __restrict__ src, __half* __restrict__ dst, int K, int N) {
+    // src [K][N] row-major -> dst [N][K] row-major (the K-major layout the tensor core reads)
+    __shared__ __half tile[32][33];
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (k < K && n < N) ? to_half<T>(src[(size_t)k * N + n]) : __float2half_rn(0.f);
     }
-    const int r = row0 + ty, cidx = col0 + tx;
-    if (r < rows_total && cidx < 2 * S) {
-        const float y = acc + bias[cidx];
-        const int b = r / E_dims, e = r % E_dims;
-        const int which = cidx / S, cs = cidx % S;
-        const int h = cs / dh, d = cs % dh;
-        __half* dst = which ? vc : kc;
-        dst[(((size_t)(b * H + h)) * E_dims + e) * dhp + d] = __float2half_rn(y);
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int n = n0 + i, k = k0 + threadIdx.x;
+        if (n < N && k < K) dst[(size_t)n * K + k] = tile[threadIdx.x][i];
     }
+}
+
+__global__ void enc_kv_scatter_kernel(const __half* __restrict__ y, __half* kc, __half* vc, int rows_total, int E_dims,
+                                      int S, int H, int dh, int dhp) {
+    // y [rows_total][2S] -> K, V caches [b][h][e][dh_pad]
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows_total * 2 * S) return;
+    const int r = (int)(i / (2 * S)), cidx = (int)(i % (2 * S));
+    const int b = r / E_dims, e = r % E_dims;
+    const int which = cidx / S, cs = cidx % S;
+    const int h = cs / dh, d = cs % dh;
+    __half* dst = which ? vc : kc;
+    dst[(((size_t)(b * H + h)) * E_dims + e) * dhp + d] = y[i];
 }
 
 }  // namespace
@@ -1085,14 +1086,16 @@ struct jk_prior {
     // arena sub-allocations for per-layer small params
     std::vector<float*> bias_ptr[4];
     std::vector<float*> ln_ptr[4];
-    std::vector<__half*> enc_w;
+    std::vector<__half*> enc_w;      // [2S][W] fp16, transposed copy of c_enc_kv.w
     std::vector<float*> enc_b;
+    __half* enc_x16;                 // [max_batch*enc_dims][W] fp16 scratch
+    __half* enc_y16;                 // [max_batch*enc_dims][2S] fp16 scratch
 };
 
 namespace {
 
 struct Layout {
-    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_sync, total;
+    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_encx, off_ency, off_sync, total;
     size_t stream_stride;
     std::vector<ushort2> cols;
     std::vector<uint32_t> soff, goff;
@@ -1219,6 +1222,12 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     L.off_prof2 = off; off = align_up(off + (size_t)kProfSlots * 8 * 8, 256);
     L.off_prof3 = off; off = align_up(off + (size_t)5 * 256 * 2 * 8, 256);
     L.off_lnacc = off; off = align_up(off + (size_t)2 * depth * 512 * 8, 256);
+    {
+        bool any6 = false;
+        for (int l = 0; l < depth; ++l) any6 = any6 || (c.attn_func[l] == 6);
+        L.off_encx = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * c.width * 2, 1024);
+        L.off_ency = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * 2 * c.n_state * 2, 1024);
+    }
     L.off_sync = off; off += 8192;
     L.total = off;
     return 0;
@@ -1273,7 +1282,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer;
+    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);
@@ -1320,6 +1329,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
             LD.enc_w = p->enc_w[l]; LD.enc_b = p->enc_b[l];
         }
     }
+    p->enc_x16 = (__half*)(A + L.off_encx); p->enc_y16 = (__half*)(A + L.off_ency);
     p->dev = (EngineDev*)(A + L.off_dev);
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_cols, L.cols.data(), L.cols.size() * sizeof(ushort2), cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_soff, L.soff.data(), L.soff.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -1377,9 +1387,9 @@ extern "C" int jk_prior_load_layer(jk_prior* p, int l, const jk_layer_weights* w
     }
     if (af == 6) {
         JK_REQUIRE(w->c_enc_kv_w && w->c_enc_kv_b, "layer %d: attn_func 6 needs c_enc_kv", l);
-        size_t n = (size_t)c.width * 2 * c.n_state;
-        if (w->w_dtype) to_half_kernel<__half><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const __half*)w->c_enc_kv_w, p->enc_w[l], n);
-        else to_half_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const float*)w->c_enc_kv_w, p->enc_w[l], n);
+        dim3 tg((2 * c.n_state + 31) / 32, (c.width + 31) / 32), tb(32, 8);
+        if (w->w_dtype) transpose_to_half_kernel<__half><<<tg, tb, 0, stream>>>((const __half*)w->c_enc_kv_w, p->enc_w[l], c.width, 2 * c.n_state);
+        else transpose_to_half_kernel<float><<<tg, tb, 0, stream>>>((const float*)w->c_enc_kv_w, p->enc_w[l], c.width, 2 * c.n_state);
         JK_CHECK_CUDA(cudaGetLastError());
         int rc = w->b_dtype ? round_bias<__half>(w->c_enc_kv_b, p->enc_b[l], 2 * c.n_state, stream)
                             : round_bias<float>(w->c_enc_kv_b, p->enc_b[l], 2 * c.n_state, stream);
@@ -1412,12 +1422,20 @@ extern "C" int jk_prior_set_encoder_kv(jk_prior* p, const float* encoder_kv, int
     const jk_prior_config& c = p->cfg;
     JK_REQUIRE(n >= 1 && n <= c.max_batch, "n_samples out of range");
     const int rows = n * c.encoder_dims;
+    JK_REQUIRE(c.width % 64 == 0, "encoder-decoder layers need width %% 64 == 0 (tcgen05 K block)");
+    {   // encoder_kv.type_as(x): fp32 -> fp16 once, shared by every enc-dec layer
+        const size_t cnt = (size_t)rows * c.width;
+        to_half_kernel<float><<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(encoder_kv, p->enc_x16, cnt);
+        JK_CHECK_CUDA(cudaGetLastError());
+    }
     for (int l = 0; l < c.depth; ++l) {
         if (c.attn_func[l] != 6) continue;
-        dim3 grid((2 * c.n_state + 31) / 32, (rows + 15) / 16), block(32, 16);
-        enc_kv_kernel<<<grid, block, 0, stream>>>(encoder_kv, p->enc_w[l], p->enc_b[l], p->host.layer[l].kc,
-                                                  p->host.layer[l].vc, rows, c.encoder_dims, c.width, c.n_state,
-                                                  c.heads, p->host.dh, p->host.dh_pad);
+        int rc = jk_conv1d_prefill_f16(p->enc_x16, p->enc_w[l], p->enc_b[l], p->enc_y16, rows, 2 * c.n_state, c.width, stream_);
+        if (rc) return rc;
+        const size_t cnt = (size_t)rows * 2 * c.n_state;
+        enc_kv_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(p->enc_y16, p->host.layer[l].kc, p->host.layer[l].vc,
+                                                                                  rows, c.encoder_dims, c.n_state, c.heads,
+                                                                                  p->host.dh, p->host.dh_pad);
         JK_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
