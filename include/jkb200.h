@@ -171,6 +171,16 @@ int jk_resblock_cl(const float* x, float* out, float* tmp, const float* w1, cons
                    const float* b2, int n, int64_t T, int C, int Cs, int dilation, float res_scale,
                    jk_stream_t stream);
 
+/* Token sampling of the autoregressive loop (prior/autoregressive.py:233-235, 343-345):
+ *   tokens[r, position] ~ Categorical(logits = logits[r, :] / temp),  r = 0..n-1
+ * one launch per position.  logits: fp32 rows `logits_stride` floats apart (entries of -inf carry no
+ * mass, so rows already passed through filter_logits are valid input); tokens: int64 [n, tok_stride].
+ * The uniform behind row r at `position` is Philox4x32-10(key = seed, counter = (position, r)), so a
+ * (seed, position, row) triple always draws the same token for the same logits. */
+int jk_sample_categorical(const float* logits, int64_t logits_stride, int n, int bins, float temp,
+                          uint64_t seed, int position, int64_t* tokens, int64_t tok_stride,
+                          jk_stream_t stream);
+
 /* torch Conv1d weight [c_out, c_in, k] (transposed = 0) or ConvTranspose1d weight
  * [c_in, c_out, k] (transposed = 1) -> packed [k, c_in, c_out] */
 int jk_pack_conv_weight(const float* w, float* packed, int c_out, int c_in, int k, int transposed,

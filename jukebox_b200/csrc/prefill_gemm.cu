@@ -24,7 +24,7 @@ using namespace jk;
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;   // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
 constexpr int kTileBytes = BM * BK * 2;                  // 16 KB per operand tile
 constexpr int kGemmThreads = 192;
 constexpr int kGemmSmem = STAGES * 2 * kTileBytes + 1024 + 256;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 prefill_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const float* __restrict__ bias, __half* __restrict__ y, int M, int N, int K) {
     extern __shared__ __align__(1024) uint8_t gsm[];

@@ -3,15 +3,16 @@
 Reference surface kept (jukebox/prior/autoregressive.py): constructor signature, parameter names
 (x_emb, pos_emb.pos_emb, start_token, transformer.*, x_out), sample(...), primed_sample(...),
 preprocess / postprocess.  Per token the host enqueues ONE kernel (embedding gather + whole
-transformer + fp32 logits, jukebox_b200/csrc/decode_engine.cu) and then the torch ops the
-reference also uses for temperature / top-k / top-p / Categorical - nothing synchronises with
-the host inside the loop (the reference's per-token `assert (0 <= x).all()` is hoisted out).
+transformer + fp32 logits, jukebox_b200/csrc/decode_engine.cu) and one sampling kernel
+(temperature + Categorical, csrc/sampling.cu; top-k / top-p keep the reference's torch filter in
+front of it) - nothing synchronises with the host inside the loop (the reference's per-token
+`assert (0 <= x).all()` is hoisted out).
 """
 import numpy as np
 import torch as t
 import torch.nn as nn
 
-from ..transformer.ops import filter_logits
+from ..transformer.ops import filter_logits, sample_categorical
 from ..transformer.transformer import Transformer
 from ..utils.logger import get_range
 
@@ -148,15 +149,21 @@ class ConditionalAutoregressive2D(nn.Module):
             lbuf, tstride = preds, self.bins
         else:
             lbuf, tstride = t.empty(N, self.bins, dtype=t.float32, device=dev), 0
+        # the key of this call's Philox stream comes from torch's default generator, so t.manual_seed /
+        # seed_per_rank make sampling reproducible exactly as they do for the reference's Categorical
+        seed = int(t.empty((), dtype=t.int64).random_().item())
         with t.no_grad():
             for sample_t in get_range(range(sample_tokens)):
                 need = get_preds or sample_t >= P
                 eng.step(N, tokens=tokens, y_cond=y_cond, x_cond=x_cond, logits=lbuf if need else None,
                          logits_tstride=tstride)
                 if sample_t >= P:
-                    x = (preds[:, sample_t] if get_preds else lbuf) / temp
-                    x = filter_logits(x, top_k=top_k, top_p=top_p)
-                    tokens[:, sample_t] = t.distributions.Categorical(logits=x, validate_args=False).sample()
+                    x = preds[:, sample_t] if get_preds else lbuf
+                    if top_k or top_p:      # filtering keeps the reference's torch expression (ops.py:99-122)
+                        x = filter_logits(x / temp, top_k=top_k, top_p=top_p).contiguous()
+                        sample_categorical(x, 1.0, seed, sample_t, tokens)
+                    else:
+                        sample_categorical(x, temp, seed, sample_t, tokens)
             for b in tr._attn_mods:
                 b.attn._advance(N, sample_tokens, fp16)
             tr.check_cache(N, sample_tokens, fp16)

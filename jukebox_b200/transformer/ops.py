@@ -75,3 +75,18 @@ def filter_logits(logits, top_k=0, top_p=0.0, filter_value=-float('Inf')):
         mask = t.zeros_like(out, dtype=t.bool).scatter_(dim=-1, index=order, src=drop)
         out[mask] = filter_value
     return out
+
+
+def sample_categorical(logits, temp, seed, position, tokens):
+    """tokens[:, position] ~ Categorical(logits = logits / temp) in one launch (jk_sample_categorical;
+    reference autoregressive.py:233-235).  logits: fp32 CUDA [N, bins] view with unit inner stride,
+    tokens: int64 CUDA [N, L].  (seed, position, row) fixes the uniform behind each draw."""
+    from .._lib import lib, check, ptr, stream_ptr
+    assert logits.dtype == t.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    assert tokens.dtype == t.int64 and tokens.dim() == 2 and tokens.stride(1) == 1
+    if not logits.is_cuda or not tokens.is_cuda:
+        raise RuntimeError("sample_categorical needs CUDA tensors (no CPU path)")
+    import ctypes as C
+    check(lib().jk_sample_categorical(C.c_void_p(logits.data_ptr()), logits.stride(0), logits.shape[0],
+                                      logits.shape[1], float(temp), C.c_uint64(seed & (2 ** 64 - 1)), int(position),
+                                      C.c_void_p(tokens.data_ptr()), tokens.stride(0), stream_ptr()))

@@ -73,3 +73,14 @@ def test_vqvae_matches_reference(tag):
         xd = orc.decode([fx[f"z{l}"]], start_level=l)
         assert xd.shape == fx[f"xd{l}"].shape
         assert rel_err(xd, fx[f"xd{l}"]) < 1e-4
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10 pin the generator behind jk_sample_categorical"""
+    from oracle.sampling_np import philox4x32_10
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, out in kat:
+        assert philox4x32_10(ctr, key) == out
