@@ -65,7 +65,7 @@ struct LayerDev {
 
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on;
+    int nslot, uni_bytes, kvpre_bytes, kv_prefetch, small_bytes, prof_on;
     float scale2;
     const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
     const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
@@ -433,44 +433,88 @@ __device__ __forceinline__ AttnGeom attn_geom(const EngineDev* E, const LayerDev
     return g;
 }
 
+// rows of one shared-memory K (or V) tile: a multiple of 16 (the MMA row block), ~24 KB per tile
 __device__ __host__ __forceinline__ int attn_tile_rows(int dhp) {
-    int r = 12288 / (dhp * 2);
-    return r < 1 ? 1 : (r > 64 ? 64 : r);
+    int r = (12288 / dhp) & ~15;
+    return r < 16 ? 16 : (r > 64 ? 64 : r);
 }
 
 // how many CTAs share one (sample, head): as few as keep every part inside ONE shared-memory tile
-// (2*TR cached rows), bounded by the grid
+// (RC - 1 cached rows + the current token's row), bounded by the grid
 __device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache) {
-    const int cap = 2 * attn_tile_rows(E->dh_pad);
+    const int cap = attn_tile_rows(E->dh_pad) - 1;
     int ns = (ncache + cap - 1) / cap;
     ns = min(ns, E->G / (B * E->H));
     return max(1, min(kMaxSplit, ns));
 }
 
+__device__ __forceinline__ void ldsm4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// K/V tiles in shared memory: row r = dhp halves, its 16-byte chunks XOR-swizzled with (r & 7) so that
+// ldmatrix (8 rows, same chunk) touches 8 different bank groups.  Only when a row has a multiple of 8
+// chunks; other head sizes stay linear (correct, bank-conflicted).
+__device__ __forceinline__ uint32_t kv_chunk_off(int r, int chunk, int dhp, int swz) {
+    return (uint32_t)(r * dhp * 2 + ((chunk ^ (r & swz)) << 4));
+}
+
+__device__ __noinline__ void attn_scores(uint32_t kt, int dhp, int swz, int nrb, int nr, uint32_t qh_s, float* sc, float scale2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npair = dhp >> 4;
+        if (warp < nrb) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const int mi = lane >> 3;
+            const int arow_i = warp * 16 + (lane & 7) + ((mi & 1) << 3);
+            const uint32_t arow = kt + arow_i * dhp * 2;
+            const int axor = arow_i & swz, ahi = mi >> 1;
+#pragma unroll 2
+            for (int ks = 0; ks < npair; ++ks) {
+                uint32_t a[4];
+                ldsm4(a, arow + (((2 * ks + ahi) ^ axor) << 4));
+                uint32_t b0 = 0u, b1 = 0u;
+                if (lane < 4) {
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(qh_s + (ks * 16 + 2 * lane) * 2));
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(qh_s + (ks * 16 + 8 + 2 * lane) * 2));
+                }
+                if (ks & 1) mma_16816(c1, a, b0, b1); else mma_16816(c0, a, b0, b1);
+            }
+            if ((lane & 3) == 0) {
+                const int rlo = warp * 16 + (lane >> 2), rhi = rlo + 8;
+                sc[rlo] = (rlo < nr) ? h2f_round(h2f_round(c0[0] + c1[0]) * scale2) : -INFINITY;
+                sc[rhi] = (rhi < nr) ? h2f_round(h2f_round(c0[2] + c1[2]) * scale2) : -INFINITY;
+            }
+        }
+}
+
 // One (sample, head, part) work item; q_len == 1 (reference factored_attention.py:82-133 and the
 // per-pattern sample branches :135-228).
-//   * the part's K and V rows are staged with cp.async - all rows in flight at once; a part that fits
-//     (<= 2*TR rows) is ONE tile, longer parts (dense / prime layers) run double-buffered TR-row tiles
-//   * scores: thread (row, slice) computes an eighth of a row's dot product, 3 shuffles finish it;
-//     s = fp16(fp16(q.k) * dh^-1/2) exactly as the reference rounds it
-//   * softmax is flash-style in fp32 (running max / sum, unnormalised P), P.V by one thread per
-//     output dimension; parts of one (sample, head) are merged by the last CTA to finish (atomic
-//     ticket), so the phase needs no extra grid barrier
+//   * the part's K and V rows are staged with cp.async into swizzled tiles; a part that fits one tile
+//     (RC-1 cached rows + the current token) is ONE tile - and may have been prefetched before the QKV
+//     GEMM - longer parts (dense / prime / enc-dec layers) run double-buffered through both tile regions
+//   * scores on the tensor cores: A = 16 key rows x 16 dims (ldmatrix), B = q in column 0, fp32
+//     accumulate; s = fp16(fp16(q.k) * dh^-1/2) exactly as the reference rounds it
+//   * softmax is flash-style in fp32 (running max / sum), every warp redundantly; P rounded to fp16 as
+//     the reference's w.half(), P.V on the tensor cores (A = P in row 0, B = V via ldmatrix.trans), each
+//     warp owning 16-dim output slices
+//   * parts of one (sample, head) are merged by the last CTA to finish (atomic ticket), so the phase
+//     needs no extra grid barrier
 __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int s, int ns,
                                        const AttnGeom G, int pslot, int pre) {
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
-    uint8_t* tiles = pre ? (jk_smem + kHeaderBytes + E->uni_bytes) : uni;   // K/V tile buffers
     float* stats = sm_stats();
     const LayerDev LD = LD_ref;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dh = E->dh, dhp = E->dh_pad, S = E->S;
-    const int nvec = dhp >> 3;
-    const int TR = attn_tile_rows(dhp);
-    const int tileB = (TR + 1) * dhp * 2;
-    float* qs = reinterpret_cast<float*>(uni + 4 * tileB);   // [dhp]
-    float* sc = qs + dhp;                                    // [2*TR + 2] scores of the tile
-    float* sp = sc + 2 * (TR + 1);                           // [2*TR + 2] exp(score - running max)
+    const int nvec = dhp >> 3, npair = dhp >> 4;
+    const int swz = (nvec & 7) ? 0 : 7;
+    const int RC = attn_tile_rows(dhp);
+    const int tileB = RC * dhp * 2;
+    const uint32_t regA = smem_u32(uni), regB = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes);
+    __half* qh = reinterpret_cast<__half*>(uni + 2 * tileB);          // [dhp]
+    float* sc = reinterpret_cast<float*>(uni + 2 * tileB + dhp * 2);  // [64] scores of the tile
     const int qkv_stride = (LD.attn_func == 6) ? S : 3 * S;
     const __half* qrow = E->qkv + (size_t)b * qkv_stride + h * dh;
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
@@ -492,38 +536,36 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
     const __half* kbase = LD.kc + (cbase + G.base) * dhp;
     const __half* vbase = LD.vc + (cbase + G.base) * dhp;
-    const bool one_shot = (i1 - i0) <= 2 * TR;
-    const int trows = one_shot ? 2 * TR : TR;
-    const int ntiles = one_shot ? 1 : (i1 - i0 + TR - 1) / TR;
-    const int voff = one_shot ? 2 * tileB : tileB;        // V buffer offset from the K buffer of a stage
+    const int trows = RC - 1;
+    const int ntiles = max(1, (i1 - i0 + trows - 1) / trows);
 
     auto issue_tile = [&](int ti) {
         const int r0 = i0 + ti * trows, nr = max(0, min(trows, i1 - r0));
-        const uint32_t kd = smem_u32(tiles + (one_shot ? 0 : (ti & 1) * 2 * tileB)), vd = kd + voff;
+        const uint32_t kd = (ti & 1) ? regB : regA, vd = kd + tileB;
         const __half* ks = kbase + (size_t)r0 * dhp;
         const __half* vs = vbase + (size_t)r0 * dhp;
 #pragma unroll 2
         for (int i = tid; i < nr * nvec; i += kConsumers) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + i * 16), "l"(ks + i * 8));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + i * 16), "l"(vs + i * 8));
+            const int r = i / nvec, c = i - r * nvec;
+            const uint32_t o = kv_chunk_off(r, c, dhp, swz);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + i * 8));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + i * 8));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (!pre) issue_tile(0);
-    for (int d = tid; d < dhp; d += kConsumers) qs[d] = (d < dh) ? ld_half_cg(qrow + d) : 0.f;
+    const bool use_pre = pre && ntiles == 1;
+    if (!use_pre) issue_tile(0);
+    for (int d = tid; d < dhp; d += kConsumers) qh[d] = (d < dh) ? __float2half_rn(ld_half_cg(qrow + d)) : __float2half_rn(0.f);
     if (!G.cur && G.wrow >= 0 && last_part) {   // patterns that do not attend the current token still cache it
         for (int d = tid; d < dh; d += kConsumers) {
             LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + S + d));
             LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
         }
     }
-    // score mapping: SL lanes share a row (SL = 8 for every real head size)
-    int SL = 1;
-    while (SL < 8 && SL * 2 <= nvec) SL <<= 1;
-    const int rr = tid / SL, sl = tid % SL, RP = kConsumers / SL;
 
     float m_run = -INFINITY, l_run = 0.f;
-    float acc[2] = {0.f, 0.f};                              // output dims tid and tid + 256
+    float* osm = sc + 64;                                  // [dhp] running output of multi-tile parts (owner-private)
+    const uint32_t qh_s = smem_u32(qh);
 #pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
         if (ti + 1 < ntiles) {
@@ -534,8 +576,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         }
         const int r0 = i0 + ti * trows;
         int nr = max(0, min(trows, i1 - r0));
-        __half* kt = reinterpret_cast<__half*>(tiles + (one_shot ? 0 : (ti & 1) * 2 * tileB));
-        __half* vt = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(kt) + voff);
+        const uint32_t kt = (use_pre || (ti & 1)) ? regB : regA, vt = kt + tileB;
         if (ti == ntiles - 1 && last_part && G.cur) {       // append the current token's k, v (from the QKV GEMM)
             for (int d = tid; d < dhp; d += kConsumers) {
                 __half kh = __float2half_rn(0.f), vh = kh;
@@ -547,82 +588,99 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
                         LD.vc[(cbase + G.wrow) * dhp + d] = vh;
                     }
                 }
-                kt[nr * dhp + d] = kh;
-                vt[nr * dhp + d] = vh;
+                const uint32_t o = kv_chunk_off(nr, d >> 3, dhp, swz) + (d & 7) * 2;
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(kt + o), "h"(__half_as_ushort(kh)));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(vt + o), "h"(__half_as_ushort(vh)));
             }
             nr += 1;
         }
+        const int nrb = (nr + 15) >> 4;                     // 16-row blocks of this tile
+        // V rows past nr inside the last row block meet P = 0 in the MMA: they must be finite
+        for (int i = tid; i < (nrb * 16 - nr) * nvec; i += kConsumers) {
+            const int r = nr + i / nvec, c = i % nvec;
+            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(vt + kv_chunk_off(r, c, dhp, swz)), "r"(0u));
+        }
         consumer_sync();
         STAMP(E, pslot, 1);
-        // ---- scores -------------------------------------------------------------------------------
-#pragma unroll 1
-        for (int base = 0; base < nr; base += RP) {
-            const int r = base + rr;
-            float dot = 0.f;
-            if (r < nr) {
-#pragma unroll 4
-                for (int v = sl; v < nvec; v += SL) {
-                    const uint4 q4 = *reinterpret_cast<const uint4*>(kt + r * dhp + v * 8);
-                    const __half2* hp = reinterpret_cast<const __half2*>(&q4);
-                    const float4 qa = *reinterpret_cast<const float4*>(qs + v * 8);
-                    const float4 qb = *reinterpret_cast<const float4*>(qs + v * 8 + 4);
-                    const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
-                    const float2 f2 = __half22float2(hp[2]), f3 = __half22float2(hp[3]);
-                    dot += qa.x * f0.x + qa.y * f0.y + qa.z * f1.x + qa.w * f1.y;
-                    dot += qb.x * f2.x + qb.y * f2.y + qb.z * f3.x + qb.w * f3.y;
-                }
-            }
-            for (int o = SL >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            if (r < nr && sl == 0) sc[r] = h2f_round(h2f_round(dot) * E->scale2);
-        }
+        // ---- scores: warp w < nrb owns key rows [16w, 16w+16) ----------------------------------------
+        attn_scores(kt, dhp, swz, nrb, nr, qh_s, sc, E->scale2);
         consumer_sync();
         STAMP(E, pslot, 2);
-        if (nr > 0) {
-            float m_t = -INFINITY;
-#pragma unroll 8
-            for (int r = 0; r < nr; ++r) m_t = fmaxf(m_t, sc[r]);
-            const float m_new = fmaxf(m_run, m_t);
-            const float corr = expf(m_run - m_new);          // exp(-inf) = 0 on the first tile
-            for (int r = tid; r < nr; r += kConsumers) sp[r] = expf(sc[r] - m_new);
-            consumer_sync();
-            m_run = m_new;
-            float lt = 0.f, a0 = acc[0] * corr, a1 = acc[1] * corr;
-            const bool d1 = tid + kConsumers < dhp;
-            if (tid < dhp) {
-#pragma unroll 8
-                for (int r = 0; r < nr; ++r) {
-                    const float pr = sp[r];
-                    lt += pr;
-                    a0 += pr * __half2float(vt[r * dhp + tid]);
-                    if (d1) a1 += pr * __half2float(vt[r * dhp + tid + kConsumers]);
-                }
-            } else {
-#pragma unroll 1
-                for (int r = 0; r < nr; ++r) lt += sp[r];
+        // ---- softmax of the tile (every warp, redundantly): lane r holds rows r and r + 32 -------------
+        const float s0 = (lane < nrb * 16) ? sc[lane] : -INFINITY;
+        const float s1 = (lane + 32 < nrb * 16) ? sc[lane + 32] : -INFINITY;
+        const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
+        const float corr = expf(m_run - m_new);              // exp(-inf) = 0 on the first tile
+        const float p0 = expf(s0 - m_new), p1 = expf(s1 - m_new);
+        l_run = l_run * corr + warp_sum(p0 + p1);
+        m_run = m_new;
+        // ---- P.V: this warp's 16-dim output slices, all row blocks.  A = P (fp16) in row 0 --------------
+        {
+            uint32_t pa0[4], pa2[4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const float src = (ks < 2) ? p0 : p1;
+                const int l0 = (ks & 1) * 16 + 2 * (lane & 3);
+                const float pa = __shfl_sync(0xffffffffu, src, l0), pb = __shfl_sync(0xffffffffu, src, l0 + 1);
+                const float pc = __shfl_sync(0xffffffffu, src, l0 + 8), pd = __shfl_sync(0xffffffffu, src, l0 + 9);
+                const __half2 h0 = __floats2half2_rn(pa, pb), h2 = __floats2half2_rn(pc, pd);
+                pa0[ks] = (lane < 4) ? *reinterpret_cast<const uint32_t*>(&h0) : 0u;
+                pa2[ks] = (lane < 4) ? *reinterpret_cast<const uint32_t*>(&h2) : 0u;
             }
-            acc[0] = a0; acc[1] = a1;
-            l_run = l_run * corr + lt;
+            const int mi = lane >> 3;
+            const int vrow_l = (lane & 7) + ((mi & 1) << 3), vhi = mi >> 1;
+            const bool last_tile = (ti == ntiles - 1);
+#pragma unroll 1
+            for (int np = warp; np < npair; np += 8) {
+                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < nrb) {
+                        const int vrow_i = ks * 16 + vrow_l;
+                        uint32_t bf[4];
+                        ldsm4_trans(bf, vt + vrow_i * dhp * 2 + (((2 * np + vhi) ^ (vrow_i & swz)) << 4));
+                        const uint32_t a[4] = {pa0[ks], 0u, pa2[ks], 0u};
+                        mma_16816(o0, a, bf[0], bf[1]);
+                        mma_16816(o1, a, bf[2], bf[3]);
+                    }
+                }
+                if (lane < 4) {      // row 0: dims np*16 + {0, 8} + 2*lane, +1
+                    const int d = np * 16 + 2 * lane;
+                    float2 r0 = make_float2(o0[0], o0[1]), r1 = make_float2(o1[0], o1[1]);
+                    if (ti > 0) {
+                        const float2 q0 = *reinterpret_cast<const float2*>(osm + d), q1 = *reinterpret_cast<const float2*>(osm + d + 8);
+                        r0.x += q0.x * corr; r0.y += q0.y * corr; r1.x += q1.x * corr; r1.y += q1.y * corr;
+                    }
+                    if (!last_tile) {
+                        *reinterpret_cast<float2*>(osm + d) = r0;
+                        *reinterpret_cast<float2*>(osm + d + 8) = r1;
+                    } else if (ns == 1) {
+                        const float inv = 1.f / l_run;
+                        __half* ao = E->a + (size_t)b * S + h * dh;
+                        if (d < dh) ao[d] = __float2half_rn(r0.x * inv);
+                        if (d + 1 < dh) ao[d + 1] = __float2half_rn(r0.y * inv);
+                        if (d + 8 < dh) ao[d + 8] = __float2half_rn(r1.x * inv);
+                        if (d + 9 < dh) ao[d + 9] = __float2half_rn(r1.y * inv);
+                    } else {
+                        float* part = E->part + ((size_t)((b * E->H + h) * kMaxSplit + s)) * (dhp + 2) + 2;
+                        *reinterpret_cast<float2*>(part + d) = r0;
+                        *reinterpret_cast<float2*>(part + d + 8) = r1;
+                    }
+                }
+            }
         }
-        if (ti + 1 < ntiles) consumer_sync();                 // tile buffers and sc/sp are reused
+        if (ti + 1 < ntiles) consumer_sync();                 // tile buffers and sc are reused
     }
     STAMP(E, pslot, 3);
     if (ns == 1) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int d = tid + u * kConsumers;
-            if (d < dh) E->a[(size_t)b * S + h * dh + d] = __float2half_rn(acc[u] / l_run);
-        }
         consumer_sync();
         return;
     }
-    // ---- split parts: publish the partial, the last finisher merges (flash-decoding merge) ----------
+    // ---- split parts: the partial is published, the last finisher merges (flash-decoding merge) ------
     const int item = b * E->H + h;
-    float* part = E->part + ((size_t)(item * kMaxSplit + s)) * (dhp + 2);
-    if (tid == 0) { part[0] = m_run; part[1] = l_run; }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int d = tid + u * kConsumers;
-        if (d < dhp) part[2 + d] = acc[u];
+    if (tid == 0) {
+        float* part = E->part + ((size_t)(item * kMaxSplit + s)) * (dhp + 2);
+        part[0] = m_run; part[1] = l_run;
     }
     consumer_sync();
     if (tid == 0) {      // acq_rel ticket: publishes this CTA's partial, acquires the others' for the merger
@@ -652,10 +710,10 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
 
 // Prefetch of the cached K/V rows of this CTA's first attention work item, issued BEFORE the QKV GEMM of
 // the layer: cached rows do not depend on the current token, so their HBM latency hides behind the
-// whole QKV phase and its barrier.  Only single-tile ("one shot") parts are prefetched; returns 1 if so.
+// whole QKV phase and its barrier.  Only single-tile parts are prefetched; returns 1 if so.
 __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t) {
     const EngineDev* E = sm_E();
-    if (E->kvpre_bytes == 0) return 0;
+    if (!E->kv_prefetch) return 0;
     const LayerDev LD = LD_ref;
     const AttnGeom G = attn_geom(E, LD, t);
     if (G.R == 0) return 0;
@@ -663,18 +721,20 @@ __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, 
     const int ns = attn_nsplit(E, B, ncache);
     if (c >= B * E->H * ns) return 0;
     const int s = c % ns, bh = c / ns, b = bh / E->H, h = bh % E->H;
-    const int dhp = E->dh_pad, nvec = dhp >> 3, TR = attn_tile_rows(dhp);
-    const int tileB = (TR + 1) * dhp * 2;
+    const int dhp = E->dh_pad, nvec = dhp >> 3, RC = attn_tile_rows(dhp);
+    const int swz = (nvec & 7) ? 0 : 7;
     const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
-    if (i1 - i0 > 2 * TR) return 0;
+    if (i1 - i0 > RC - 1) return 0;
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
     const __half* ks = LD.kc + (cbase + G.base + i0) * dhp;
     const __half* vs = LD.vc + (cbase + G.base + i0) * dhp;
-    const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + 2 * tileB;
+    const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + RC * dhp * 2;
 #pragma unroll 2
     for (int i = threadIdx.x; i < (i1 - i0) * nvec; i += kConsumers) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + i * 16), "l"(ks + i * 8));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + i * 16), "l"(vs + i * 8));
+        const int r = i / nvec, cc = i - r * nvec;
+        const uint32_t o = kv_chunk_off(r, cc, dhp, swz);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + i * 8));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + i * 8));
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     return 1;
@@ -928,11 +988,14 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
         const int pre_ok = attn_prefetch(LD, B, c, t);
-        GemmArgs ga;
-        ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
-        ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-        ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
-        ring = gemm_phase(ring, B, ga);
+        // a fresh argument record per phase: nothing of it stays live across the calls in between
+        {
+            GemmArgs ga;
+            ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
+            ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
+            ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
+            ring = gemm_phase(ring, B, ga);
+        }
         // next layer's record + column assignment -> the other shared-memory slot.  The descriptor is in
         // HBM (the weight stream evicts it from L2 every step): issue the loads here so their latency hides
         // behind the barrier instead of sitting on the dependency chain.
@@ -955,20 +1018,30 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             GRID_BARRIER();
         }
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
-        ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
-        ga.pslot = (int)nbar; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
-        ring = gemm_phase(ring, B, ga);
+        {
+            GemmArgs ga;
+            ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
+            ga.pslot = (int)nbar; ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
+            ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
+            ring = gemm_phase(ring, B, ga);
+        }
         GRID_BARRIER();
-        ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
-        ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-        ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
-        ring = gemm_phase(ring, B, ga);
+        {
+            GemmArgs ga;
+            ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
+            ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
+            ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
+            ring = gemm_phase(ring, B, ga);
+        }
         GRID_BARRIER();
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l + 1) * 512 + 16 * tid] = 0;  // LN1 statistics are consumed
-        ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
-        ga.pslot = (int)nbar; ga.bias = LD.b_2; ga.ln_in = nullptr;
-        ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
-        ring = gemm_phase(ring, B, ga);
+        {
+            GemmArgs ga;
+            ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
+            ga.pslot = (int)nbar; ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
+            ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
+            ring = gemm_phase(ring, B, ga);
+        }
         GRID_BARRIER();
     }
     if (A.h_out) {
@@ -1104,7 +1177,7 @@ struct Layout {
     std::vector<size_t> cache_bytes;
     std::vector<int> cache_rows;
     size_t small_per_layer;
-    int dh, dh_pad, bc, prime_pad, uni_bytes, kvpre_bytes, nslot, smem_bytes;
+    int dh, dh_pad, bc, prime_pad, uni_bytes, kvpre_bytes, kv_prefetch, nslot, smem_bytes;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1128,7 +1201,7 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
                "width/n_state/mlp_width must be multiples of 16 (got %d/%d/%d)", c.width, c.n_state, c.mlp_width);
     JK_REQUIRE(c.n_state % c.heads == 0, "n_state %% heads != 0");
     L.dh = c.n_state / c.heads;
-    L.dh_pad = (int)align_up(L.dh, 8);
+    L.dh_pad = (int)align_up(L.dh, 16);      // MMA k-steps / output pairs of 16 dims
     JK_REQUIRE(L.dh_pad <= 512, "head_dim %d > 512 unsupported", L.dh);
     L.bc = c.blocks > 0 ? c.n_ctx / c.blocks : c.n_ctx;
     JK_REQUIRE(c.blocks == 0 || c.n_ctx % c.blocks == 0, "n_ctx %% blocks != 0");
@@ -1177,13 +1250,14 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     size_t uni = (size_t)16 * (Kmax + 8) * 2;
     uni = std::max(uni, (size_t)16 * kLogitKT * 4);
     uni = std::max(uni, (size_t)8 * 8 * 16 * 8 * 4);                              // cross-warp reduction
-    const int TR = attn_tile_rows(L.dh_pad);
-    size_t attn = (size_t)4 * (TR + 1) * L.dh_pad * 2 + (size_t)(L.dh_pad + 4 * (TR + 1)) * 4 + 64;
+    const int RC = attn_tile_rows(L.dh_pad);
+    const size_t kv_stage = (size_t)2 * RC * L.dh_pad * 2;                        // one K tile + one V tile
+    size_t attn = kv_stage + (size_t)L.dh_pad * 2 + 64 * 4 + (size_t)L.dh_pad * 4 + 64;   // tiles, q, scores, running output
     uni = std::max(uni, attn);
     L.uni_bytes = (int)align_up(uni, 1024);
     const int max_smem = 232448;
-    L.kvpre_bytes = (int)align_up((size_t)4 * (TR + 1) * L.dh_pad * 2, 1024);
-    if (getenv("JK_NO_KV_PREFETCH") || (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes < 4) L.kvpre_bytes = 0;
+    L.kvpre_bytes = (int)align_up(kv_stage, 1024);      // second K/V stage: prefetch target / double buffer
+    L.kv_prefetch = getenv("JK_NO_KV_PREFETCH") ? 0 : 1;
     int nslot = (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes;
     nslot = std::min(nslot, kMaxSlots);
     JK_REQUIRE(nslot >= 2, "not enough shared memory for the weight ring (uni %d bytes)", L.uni_bytes);
@@ -1282,7 +1356,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
+    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.kv_prefetch = L.kv_prefetch; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);
