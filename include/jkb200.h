@@ -117,6 +117,29 @@ typedef struct jk_step_args {
     int64_t logits_tstride;       /* 0 to overwrite the same [n, bins] buffer every step */
 } jk_step_args;
 
+/* Chunked prefill of the given (prime) tokens: positions 0 .. n_positions-1 of every sample through all
+ * layers in one call - the chunked half of ConditionalAutoregressive2D.primed_sample
+ * (prior/autoregressive.py:251-359), whose own check_chunks asserts it equals stepping token by token.
+ * The four Conv1Ds of each layer run as [n_samples * n_positions, K] x [K, N] GEMMs on tcgen05.  On return
+ * the engine stands at position n_positions (K/V caches filled), exactly as after that many jk_prior_step
+ * calls.  tokens[b * tok_stride + t] is the token AT position t (the input of position t+1), as in
+ * jk_step_args; h_out (optional, fp32 [n_samples, n_positions, width]) receives the transformer output -
+ * the `only_encode` forward of the lyric encoder (prior/prior.py:285-301). */
+typedef struct jk_prefill_args {
+    int32_t n_samples;
+    int32_t n_positions;
+    const int64_t* tokens;
+    int64_t tok_stride;
+    const float* y_cond;      /* [n_samples, width] or NULL (start token) */
+    const float* x_cond;      /* [n_samples, x_cond_len, width] or NULL */
+    int64_t x_cond_len;       /* 1 or n_ctx */
+    float* h_out;
+} jk_prefill_args;
+/* positions one prefill call can take; 0 when the configuration has no tensor-core prefill (a GEMM K that
+ * is not a multiple of 64, or encoder-decoder layers): step the given tokens instead */
+int jk_prior_prefill_capacity(const jk_prior* p, int* max_positions);
+int jk_prior_prefill(jk_prior* p, const jk_prefill_args* args, jk_stream_t stream);
+
 /* one token position; increments the device-side position counter */
 int jk_prior_step(jk_prior* p, const jk_step_args* a, jk_stream_t stream);
 /* current position (host copy of the device counter as tracked by the calls made so far) */

@@ -36,6 +36,12 @@ class StepArgs(C.Structure):
                 ("logits_bstride", C.c_int64), ("logits_tstride", C.c_int64)]
 
 
+class PrefillArgs(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("n_positions", C.c_int32), ("tokens", C.c_void_p),
+                ("tok_stride", C.c_int64), ("y_cond", C.c_void_p), ("x_cond", C.c_void_p),
+                ("x_cond_len", C.c_int64), ("h_out", C.c_void_p)]
+
+
 class ConvArgs(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("t_in", C.c_int64), ("c_in", C.c_int32),
                 ("out", C.c_void_p), ("t_out", C.c_int64), ("c_out", C.c_int32),
@@ -59,6 +65,8 @@ SIGNATURES = {
     "jk_prior_reset": (_I, [_P, _I, _P]),
     "jk_prior_set_encoder_kv": (_I, [_P, _P, _I, _P]),
     "jk_prior_step": (_I, [_P, C.POINTER(StepArgs), _P]),
+    "jk_prior_prefill_capacity": (_I, [_P, C.POINTER(C.c_int)]),
+    "jk_prior_prefill": (_I, [_P, C.POINTER(PrefillArgs), _P]),
     "jk_prior_position": (_I, [_P, C.POINTER(C.c_int)]),
     "jk_prior_debug_buffer": (_I, [_P, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "jk_conv1d_prefill_f16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

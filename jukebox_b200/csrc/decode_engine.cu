@@ -27,8 +27,7 @@
 //     contiguous run (transpose-block layers store position p at row (p % bc)*blocks + p / bc).
 //
 // Numerics: activations fp16, accumulation fp32, LayerNorm/softmax fp32 - see oracle/transformer_np.py.
-#include "common.cuh"
-#include "../../include/jkb200.h"
+#include "engine.cuh"
 #include <cooperative_groups.h>
 #include <vector>
 #include <algorithm>
@@ -51,41 +50,6 @@ constexpr int kLogitRowsPerPass = 8;
 constexpr int kMaxSplit = 8;
 constexpr int kProfSlots = 1024;
 constexpr int kBarGroup = 12;           // CTAs per first-level barrier counter
-
-struct LayerDev {
-    int attn_func;
-    int rows;                       // cache rows per (b, h)
-    __half* kc;
-    __half* vc;                     // [B][H][rows][dh_pad]
-    const float *ln0_g, *ln0_b, *ln1_g, *ln1_b;
-    const float *b_qkv, *b_o, *b_1, *b_2;   // fp32 holding fp16-rounded biases
-    const __half* enc_w;            // [W][2S] fp16 copy of c_enc_kv.w (attn_func 6)
-    const float* enc_b;
-};
-
-struct EngineDev {
-    int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes, kvpre_bytes, kv_prefetch, small_bytes, prof_on;
-    float scale2;
-    const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
-    const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
-    const uint8_t* streams;
-    unsigned long long stream_stride;
-    __half *h, *qkv, *a, *x1, *g;   // [16][.] fp16 activations
-    float* part;                    // split-KV partials [Bmax*H*kMaxSplit][dh_pad + 2]
-    unsigned* acnt;                 // [Bmax*H] merge tickets
-    long long* lnacc;               // [2*depth][16][2] fixed-point LayerNorm accumulators (sum, sumsq)
-    int split_rows;                 // attention: rows per part before a (sample, head) is split over CTAs
-    long long* prof2;               // [kProfSlots][8] intra-phase clock64 stamps of CTA 0 (tuning aid)
-    unsigned long long* prof3;      // [5][256][2] per-CTA barrier arrival / exit times of layer 1
-    unsigned long long* prof;       // [kProfSlots] phase timestamps of CTA 0 (globaltimer ns)
-    unsigned* bar;
-    unsigned* epoch;
-    int* t;
-    const float *x_emb, *pos_emb, *x_out, *start_token;
-    const int* lrow0;               // [G+1] logits rows per CTA (prefix)
-    LayerDev layer[JK_MAX_DEPTH];
-};
 
 struct StepArgs {
     int n;
@@ -110,8 +74,6 @@ __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64
 __device__ __forceinline__ float* sm_stats() { return reinterpret_cast<float*>(jk_smem + 256); }
 __device__ __forceinline__ long long* sm_sacc() { return reinterpret_cast<long long*>(jk_smem + 512); }
 __device__ __forceinline__ uint8_t* sm_uni() { return jk_smem + kHeaderBytes; }
-struct EngineDev;
-struct LayerDev;
 // The engine descriptor lives in global memory; with the shared-memory carve-out at its maximum there is
 // no L1 to cache it, so every `E->field` was an L2 round trip (~300 cycles) on the dependency chain.
 // The head of the descriptor (everything before the per-layer array) and the current / next layer
@@ -1143,32 +1105,12 @@ __global__ void enc_kv_scatter_kernel(const __half* __restrict__ y, __half* kc, 
 // =========================================================================================
 // host side
 // =========================================================================================
-struct jk_prior {
-    jk_prior_config cfg;
-    EngineDev host;            // host mirror of the device struct
-    EngineDev* dev;            // in arena
-    uint8_t* arena;
-    size_t arena_bytes;
-    int G;
-    int smem_bytes;
-    int t_host;
-    std::vector<ushort2> cols;
-    std::vector<uint32_t> goff;      // [G][depth][4] per-GEMM stream offsets (16-B units)
-    uint32_t* d_goff;
-    ushort2* d_cols;
-    // arena sub-allocations for per-layer small params
-    std::vector<float*> bias_ptr[4];
-    std::vector<float*> ln_ptr[4];
-    std::vector<__half*> enc_w;      // [2S][W] fp16, transposed copy of c_enc_kv.w
-    std::vector<float*> enc_b;
-    __half* enc_x16;                 // [max_batch*enc_dims][W] fp16 scratch
-    __half* enc_y16;                 // [max_batch*enc_dims][2S] fp16 scratch
-};
-
 namespace {
 
 struct Layout {
-    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_encx, off_ency, off_sync, total;
+    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_encx, off_ency, off_wt, off_pf, off_sync, total;
+    size_t wt_per_layer;
+    int pf_len, pf_rows;
     size_t stream_stride;
     std::vector<ushort2> cols;
     std::vector<uint32_t> soff, goff;
@@ -1304,6 +1246,17 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
         L.off_encx = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * c.width * 2, 1024);
         L.off_ency = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * 2 * c.n_state * 2, 1024);
     }
+    {   // chunked prefill: K-major fp16 weight copies + activation workspace (prefill.cu).  Needs every GEMM K to
+        // be a multiple of the tcgen05 K block (64) and no encoder-decoder layer; else pf_rows = 0.
+        bool ok = (c.width % 64 == 0) && (c.n_state % 64 == 0) && (c.mlp_width % 64 == 0) && !getenv("JK_NO_PREFILL");
+        for (int l = 0; l < depth; ++l) ok = ok && (c.attn_func[l] != 6);
+        L.pf_len = ok ? std::min(c.n_ctx, 512) : 0;
+        L.pf_rows = c.max_batch * L.pf_len;
+        L.wt_per_layer = align_up((size_t)(3 * c.n_state * c.width + c.width * c.n_state + 2 * c.mlp_width * c.width) * 2, 1024);
+        L.off_wt = off; if (ok) off = align_up(off + L.wt_per_layer * depth, 1024);
+        L.off_pf = off;
+        if (ok) off = align_up(off + (size_t)L.pf_rows * (3 * c.width + 3 * c.n_state + c.n_state + c.mlp_width) * 2, 1024);
+    }
     L.off_sync = off; off += 8192;
     L.total = off;
     return 0;
@@ -1406,6 +1359,25 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
         }
     }
     p->enc_x16 = (__half*)(A + L.off_encx); p->enc_y16 = (__half*)(A + L.off_ency);
+    p->pf_rows = L.pf_rows; p->pf_len = L.pf_len;
+    for (int i = 0; i < 4; ++i) p->wt[i].assign(cfg->depth, nullptr);
+    if (L.pf_rows) {
+        for (int l = 0; l < cfg->depth; ++l) {
+            __half* w = (__half*)(A + L.off_wt + L.wt_per_layer * l);
+            p->wt[0][l] = w; w += (size_t)3 * cfg->n_state * cfg->width;
+            p->wt[1][l] = w; w += (size_t)cfg->width * cfg->n_state;
+            p->wt[2][l] = w; w += (size_t)cfg->mlp_width * cfg->width;
+            p->wt[3][l] = w;
+        }
+        __half* a = (__half*)(A + L.off_pf);
+        const size_t R = (size_t)L.pf_rows;
+        p->pf_x = a; a += R * cfg->width;
+        p->pf_xn = a; a += R * cfg->width;
+        p->pf_x1 = a; a += R * cfg->width;
+        p->pf_qkv = a; a += R * 3 * cfg->n_state;
+        p->pf_a = a; a += R * cfg->n_state;
+        p->pf_g = a;
+    }
     p->dev = (EngineDev*)(A + L.off_dev);
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_cols, L.cols.data(), L.cols.size() * sizeof(ushort2), cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_soff, L.soff.data(), L.soff.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -1455,6 +1427,14 @@ extern "C" int jk_prior_load_layer(jk_prior* p, int l, const jk_layer_weights* w
         rc = w->b_dtype ? round_bias<__half>(bs[gi], p->bias_ptr[gi][l], Ns[gi], stream)
                         : round_bias<float>(bs[gi], p->bias_ptr[gi][l], Ns[gi], stream);
         if (rc) return rc;
+    }
+    if (p->pf_rows) {      // K-major fp16 copies for the tensor-core prefill
+        for (int gi = 0; gi < 4; ++gi) {
+            dim3 tg((Ns[gi] + 31) / 32, (Ks[gi] + 31) / 32), tb(32, 8);
+            if (w->w_dtype) transpose_to_half_kernel<__half><<<tg, tb, 0, stream>>>((const __half*)ws[gi], p->wt[gi][l], Ks[gi], Ns[gi]);
+            else transpose_to_half_kernel<float><<<tg, tb, 0, stream>>>((const float*)ws[gi], p->wt[gi][l], Ks[gi], Ns[gi]);
+            JK_CHECK_CUDA(cudaGetLastError());
+        }
     }
     const float* lns[4] = {w->ln0_g, w->ln0_b, w->ln1_g, w->ln1_b};
     for (int i = 0; i < 4; ++i) {

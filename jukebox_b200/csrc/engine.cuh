@@ -1,0 +1,76 @@
+// Engine descriptor shared by the decode kernel (decode_engine.cu) and the chunked prefill (prefill.cu).
+#pragma once
+#include "common.cuh"
+#include "../../include/jkb200.h"
+#include <vector>
+
+namespace jk {
+
+struct LayerDev {
+    int attn_func;
+    int rows;                       // cache rows per (b, h)
+    __half* kc;
+    __half* vc;                     // [B][H][rows][dh_pad]
+    const float *ln0_g, *ln0_b, *ln1_g, *ln1_b;
+    const float *b_qkv, *b_o, *b_1, *b_2;   // fp32 holding fp16-rounded biases
+    const __half* enc_w;            // [W][2S] fp16 copy of c_enc_kv.w (attn_func 6)
+    const float* enc_b;
+};
+
+struct EngineDev {
+    int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
+    int nslot, uni_bytes, kvpre_bytes, kv_prefetch, small_bytes, prof_on;
+    float scale2;
+    const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
+    const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
+    const uint8_t* streams;
+    unsigned long long stream_stride;
+    __half *h, *qkv, *a, *x1, *g;   // [16][.] fp16 activations
+    float* part;                    // split-KV partials [Bmax*H*kMaxSplit][dh_pad + 2]
+    unsigned* acnt;                 // [Bmax*H] merge tickets
+    long long* lnacc;               // [2*depth][16][2] fixed-point LayerNorm accumulators (sum, sumsq)
+    int split_rows;                 // attention: rows per part before a (sample, head) is split over CTAs
+    long long* prof2;               // [kProfSlots][8] intra-phase clock64 stamps of CTA 0 (tuning aid)
+    unsigned long long* prof3;      // [5][256][2] per-CTA barrier arrival / exit times of layer 1
+    unsigned long long* prof;       // [kProfSlots] phase timestamps of CTA 0 (globaltimer ns)
+    unsigned* bar;
+    unsigned* epoch;
+    int* t;
+    const float *x_emb, *pos_emb, *x_out, *start_token;
+    const int* lrow0;               // [G+1] logits rows per CTA (prefix)
+    LayerDev layer[JK_MAX_DEPTH];
+};
+
+// prefill_gemm.cu: Y = epi(X . W^T + bias [, res]) on tcgen05; w_t is [N, K] fp16.
+//   epi 0: fp16(acc + b)   1: fp16(quick_gelu(fp16(acc + b)))   2: fp16(res + fp16(acc + b))
+int gemm_f16_tc(const void* x, const void* w_t, const float* bias, const void* res, void* y, int M, int N, int K,
+                int epi, cudaStream_t stream);
+
+}  // namespace jk
+
+struct jk_prior {
+    jk_prior_config cfg;
+    jk::EngineDev host;            // host mirror of the device struct
+    jk::EngineDev* dev;            // in arena
+    uint8_t* arena;
+    size_t arena_bytes;
+    int G;
+    int smem_bytes;
+    int t_host;
+    std::vector<ushort2> cols;
+    std::vector<uint32_t> goff;      // [G][depth][4] per-GEMM stream offsets (16-B units)
+    uint32_t* d_goff;
+    ushort2* d_cols;
+    // arena sub-allocations for per-layer small params
+    std::vector<float*> bias_ptr[4];
+    std::vector<float*> ln_ptr[4];
+    std::vector<__half*> enc_w;      // [2S][W] fp16, transposed copy of c_enc_kv.w
+    std::vector<float*> enc_b;
+    __half* enc_x16;                 // [max_batch*enc_dims][W] fp16 scratch
+    __half* enc_y16;                 // [max_batch*enc_dims][2S] fp16 scratch
+    // chunked prefill (prefill.cu): K-major fp16 copies of the four Conv1D weights of every layer and the
+    // [pf_rows x .] activation workspace; pf_rows = 0 when the configuration cannot use the tensor-core path
+    std::vector<__half*> wt[4];      // [N][K]
+    int pf_rows, pf_len;             // workspace rows (= max_batch * pf_len), positions per prefill
+    __half *pf_x, *pf_xn, *pf_qkv, *pf_a, *pf_x1, *pf_g;
+};

@@ -16,8 +16,7 @@
 //                           out-of-bounds loads)
 // W is supplied transposed ([N, K], K contiguous) - the engine packs it once at weight load - so both
 // operands are K-major, the layout the tensor core reads without a transpose bit.
-#include "common.cuh"
-#include "../../include/jkb200.h"
+#include "engine.cuh"
 #include <cuda.h>
 
 using namespace jk;
@@ -65,9 +64,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// The decode kernel's epilogues (decode_engine.cu gemm_phase), same fp16 rounding points:
+//   0  Conv1D output rounded once from the fp32 accumulator           (ops.py:83-96)
+//   1  quick_gelu with the reference's three fp16 roundings           (ops.py:33-35)
+//   2  residual add in fp16                                           (transformer.py:82-83)
+__device__ __forceinline__ __half epilogue_value(float acc, float bias, float res, int epi) {
+    const float y = h2f_round(acc + bias);
+    if (epi == 1) {
+        const float z = h2f_round(1.702f * y);
+        const float sg = h2f_round(1.0f / (1.0f + expf(-z)));
+        return __float2half_rn(y * sg);
+    }
+    if (epi == 2) return __float2half_rn(res + y);
+    return __float2half_rn(y);
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 2)
 prefill_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                    const float* __restrict__ bias, __half* __restrict__ y, int M, int N, int K) {
+                    const float* __restrict__ bias, const __half* __restrict__ res, __half* __restrict__ y, int M, int N,
+                    int K, int epi) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     uint8_t* tiles = gsm;                                               // [STAGES][A | B]
     uint64_t* full = reinterpret_cast<uint64_t*>(gsm + STAGES * 2 * kTileBytes);
@@ -140,21 +155,25 @@ prefill_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < M) {
                 __half* yr = y + (size_t)row * N + n0 + c0;
+                const __half* rr = res ? res + (size_t)row * N + n0 + c0 : nullptr;
                 if (n0 + c0 + 32 <= N && (N & 7) == 0) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        __half2 h[4];
+                        uint4 rv = make_uint4(0, 0, 0, 0);
+                        if (epi == 2) rv = *reinterpret_cast<const uint4*>(rr + v * 8);
+                        const __half* rh = reinterpret_cast<const __half*>(&rv);
+                        __half h[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = v * 8 + e * 2;
-                            const float b0f = bias ? bias[n0 + c0 + c] : 0.f, b1f = bias ? bias[n0 + c0 + c + 1] : 0.f;
-                            h[e] = __floats2half2_rn(__uint_as_float(r[c]) + b0f, __uint_as_float(r[c + 1]) + b1f);
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = v * 8 + e;
+                            h[e] = epilogue_value(__uint_as_float(r[c]), bias ? bias[n0 + c0 + c] : 0.f, __half2float(rh[e]), epi);
                         }
                         *reinterpret_cast<uint4*>(yr + v * 8) = *reinterpret_cast<uint4*>(h);
                     }
                 } else {
                     for (int c = 0; c < 32 && n0 + c0 + c < N; ++c)
-                        yr[c] = __float2half_rn(__uint_as_float(r[c]) + (bias ? bias[n0 + c0 + c] : 0.f));
+                        yr[c] = epilogue_value(__uint_as_float(r[c]), bias ? bias[n0 + c0 + c] : 0.f,
+                                               epi == 2 ? __half2float(rr[c]) : 0.f, epi);
                 }
             }
         }
@@ -200,12 +219,12 @@ int make_map(CUtensorMap* map, const void* base, int rows, int K) {
 
 }  // namespace
 
-extern "C" int jk_conv1d_prefill_f16(const void* x, const void* w_t, const float* bias, void* y, int M, int N, int K,
-                                     jk_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int jk::gemm_f16_tc(const void* x, const void* w_t, const float* bias, const void* res, void* y, int M, int N, int K,
+                    int epi, cudaStream_t stream) {
     JK_REQUIRE(x && w_t && y, "null argument");
     JK_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % BK == 0, "prefill GEMM needs K to be a multiple of %d (got M %d N %d K %d)", BK, M, N, K);
-    JK_REQUIRE((((uintptr_t)x | (uintptr_t)w_t | (uintptr_t)y) & 15) == 0, "operands must be 16-byte aligned");
+    JK_REQUIRE((((uintptr_t)x | (uintptr_t)w_t | (uintptr_t)y | (uintptr_t)res) & 15) == 0, "operands must be 16-byte aligned");
+    JK_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || res), "bad epilogue");
     CUtensorMap mx, mw;
     int rc = make_map(&mx, x, M, K);
     if (rc) return rc;
@@ -217,7 +236,12 @@ extern "C" int jk_conv1d_prefill_f16(const void* x, const void* w_t, const float
         attr_set = true;
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    prefill_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(mx, mw, bias, (__half*)y, M, N, K);
+    prefill_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(mx, mw, bias, (const __half*)res, (__half*)y, M, N, K, epi);
     JK_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int jk_conv1d_prefill_f16(const void* x, const void* w_t, const float* bias, void* y, int M, int N, int K,
+                                     jk_stream_t stream_) {
+    return jk::gemm_f16_tc(x, w_t, bias, nullptr, y, M, N, K, 0, (cudaStream_t)stream_);
 }

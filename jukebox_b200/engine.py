@@ -112,6 +112,29 @@ class DecodeEngine:
         with torch.cuda.device(self.device):
             check(lib().jk_prior_set_encoder_kv(self.handle, ptr(enc), enc.shape[0], stream_ptr()))
 
+    # ---- chunked prefill ---------------------------------------------------------------
+    @property
+    def prefill_capacity(self):
+        """positions one `prefill` call can take (0: this configuration steps its given tokens)"""
+        out = C.c_int(0)
+        check(lib().jk_prior_prefill_capacity(self.handle, C.byref(out)))
+        return out.value
+
+    def prefill(self, n, n_positions, *, tokens=None, y_cond=None, x_cond=None, h_out=None):
+        """positions 0..n_positions-1 of all samples through every layer at once (tcgen05 GEMMs);
+        afterwards the engine is at position n_positions."""
+        a = _lib.PrefillArgs()
+        a.n_samples, a.n_positions = n, n_positions
+        a.tokens = ptr(tokens)
+        a.tok_stride = tokens.stride(0) if tokens is not None else 0
+        a.y_cond = ptr(y_cond)
+        a.x_cond = ptr(x_cond)
+        a.x_cond_len = x_cond.shape[1] if x_cond is not None else 1
+        a.h_out = ptr(h_out)
+        with torch.cuda.device(self.device):
+            check(lib().jk_prior_prefill(self.handle, C.byref(a), stream_ptr()))
+        self.position = n_positions
+
     # ---- one token -----------------------------------------------------------------------
     def step(self, n, *, x_in=None, tokens=None, y_cond=None, x_cond=None, h_out=None, logits=None,
              logits_tstride=0):

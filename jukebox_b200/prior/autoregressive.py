@@ -153,7 +153,13 @@ class ConditionalAutoregressive2D(nn.Module):
         # seed_per_rank make sampling reproducible exactly as they do for the reference's Categorical
         seed = int(t.empty((), dtype=t.int64).random_().item())
         with t.no_grad():
-            for sample_t in get_range(range(sample_tokens)):
+            start = 0
+            if P > 1 and not get_preds and 1 < P <= eng.prefill_capacity:
+                # the given tokens go through all layers at once (the reference's chunked primed_sample,
+                # autoregressive.py:300-338); chunk_size is moot - one chunk
+                eng.prefill(N, P, tokens=tokens, y_cond=y_cond, x_cond=x_cond)
+                start = P
+            for sample_t in get_range(range(start, sample_tokens)):
                 need = get_preds or sample_t >= P
                 eng.step(N, tokens=tokens, y_cond=y_cond, x_cond=x_cond, logits=lbuf if need else None,
                          logits_tstride=tstride)
@@ -207,10 +213,13 @@ class ConditionalAutoregressive2D(nn.Module):
             self.transformer.del_cache()
             acts = t.empty(N, D, self.width, dtype=t.float32, device=x.device)
             x = x.contiguous()
-            for i in range(D):
-                out = t.empty(N, self.width, dtype=t.float32, device=x.device)
-                eng.step(N, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=out)
-                acts[:, i] = out
+            if 1 < D <= eng.prefill_capacity:
+                eng.prefill(N, D, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=acts)
+            else:
+                for i in range(D):
+                    out = t.empty(N, self.width, dtype=t.float32, device=x.device)
+                    eng.step(N, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=out)
+                    acts[:, i] = out
             self.transformer.del_cache()
             if self.add_cond_after_transformer and x_cond is not None:
                 acts = acts + x_cond
