@@ -188,6 +188,11 @@ def cpu_baseline(prior_state, cfg, n, tokens, seed=0):
     """oracle (numpy fp32 restatement of the reference's CA2D.sample body) on the host cores"""
     import numpy as np
     from oracle.transformer_np import PriorOracle
+    try:        # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core through BLAS
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     orc = PriorOracle(prior_state, cfg["input_dims"], cfg["bins"], cfg["width"], cfg["depth"], cfg["heads"],
                       attn_order=12, blocks=cfg["blocks"], x_cond=True, y_cond=True, prime_len=cfg["prime_len"])
     rng = np.random.RandomState(seed)
@@ -487,7 +492,7 @@ def main():
                          d2h_bytes_per_step=int(z_host.numel() * 8), ms_per_step=ms_e2e / args.steps,
                          api="SimplePrior.sample(n_samples, z=None, z_conds=None, y, fp16=True, temp=0.99, chunk_size=32)"),
                 gpu_launches=int(launches_timed), roofline=roof, clocks=clocks)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (bounded sample, rank 0)
         sd, cfg = oracle_state_from(prior)
         v, dt = cpu_baseline(sd, cfg, n, args.cpu_tokens)
         line["cpu_baseline"] = dict(value=v, unit="tokens/s", cores=os.cpu_count(), kind="port",
