@@ -189,7 +189,9 @@ typedef struct jk_conv_args {
 int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream);
 
 /* ResConv1DBlock (vqvae/resnet.py:27-44): out = x + res_scale * (W2.relu(W1 *_dil relu(x) + b1) + b2)
- * x, out [n, T, C]; tmp [n, T, Cs] scratch; w1 packed [3, C, Cs]; w2 packed [1, Cs, C]. */
+ * x, out [n, T, C] (x != out); w1 packed [3, C, Cs]; w2 packed [1, Cs, C].  For C == Cs in {32, 64} (every
+ * ResConv1DBlock of the reference's VQ-VAEs) this is ONE launch with the hidden activation kept in shared memory and
+ * tmp may be NULL; other shapes run as two jk_conv1d_cl launches through tmp [n, T, Cs]. */
 int jk_resblock_cl(const float* x, float* out, float* tmp, const float* w1, const float* b1, const float* w2,
                    const float* b2, int n, int64_t T, int C, int Cs, int dilation, float res_scale,
                    jk_stream_t stream);

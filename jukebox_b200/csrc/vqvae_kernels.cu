@@ -5,6 +5,7 @@
 // The encoder feeds an argmin whose indices must be bit-exact, so these kernels keep true fp32 FMA
 // arithmetic (no TF32): see DESIGN.md "VQ-VAE numerics".
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/jkb200.h"
 
 using namespace jk;
@@ -210,6 +211,165 @@ __global__ void __launch_bounds__(256) conv1d_cl_kernel(ConvP P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused ResConv1DBlock (resnet.py:27-44) for the VQ-VAE's own shapes (n_in == n_state == C, C = 32 or 64):
+//   out = x + res_scale * (W2 . relu(W1 (*) relu(x) + b1) + b2),   W1: 3 taps with dilation d, W2: 1 x 1
+// One CTA = one tile of TT positions of one clip.  Both weight matrices, the three (relu'd) input tap tiles and
+// the hidden tile live in shared memory; the hidden activation never goes to HBM (the two-launch form wrote
+// and re-read it: 2 x 4 x C bytes per position of 5 x 4 x C).  Each thread owns 8 positions x 4 channels; per
+// 4 k-steps it issues 8 + 4 LDS.128 for 128 FMAs (the generic kernel: 20 LDS for 64), with the position
+// mapping (ty + TY * i) chosen so that the lanes of a warp read at most TX-strided rows 1 apart: no bank
+// conflicts with the 4-float row padding.  fp32 FMAs in the generic kernel's order (tap, then input channel),
+// so both paths agree to the last bit on everything before the residual add.
+// ---------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256, 1)
+resblock_fused_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w1,
+                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                      long long T, int dil, float rs) {
+    constexpr int TX = C / 4, TY = 256 / TX, TT = TY * 8, XS = C + 4;
+    extern __shared__ __align__(16) float rsm[];
+    float* w1s = rsm;                    // [3][C][C]
+    float* w2s = w1s + 3 * C * C;        // [C][C]
+    float* xs = w2s + C * C;             // [3][TT][XS]  relu(x) at t + (tap - 1) * dil
+    float* hs = xs + 3 * TT * XS;        // [TT][XS]     relu(hidden)
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    const long long t0 = (long long)blockIdx.x * TT;
+    const float* xin = x + (size_t)blockIdx.y * T * C;
+    float* xout = out + (size_t)blockIdx.y * T * C;
+    for (int i = tid; i < 3 * C * C / 4; i += 256) reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(w1) + i);
+    for (int i = tid; i < C * C / 4; i += 256) reinterpret_cast<float4*>(w2s)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+        const long long off = (long long)(tap - 1) * dil;
+#pragma unroll 4
+        for (int i = tid; i < TT * TX; i += 256) {
+            const int t = i / TX, c4 = i % TX;
+            const long long tp = t0 + t + off;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp >= 0 && tp < T) v = __ldg(reinterpret_cast<const float4*>(xin + (size_t)tp * C) + c4);
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            *reinterpret_cast<float4*>(xs + ((size_t)tap * TT + t) * XS + c4 * 4) = v;
+        }
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#define JK_RB_STEP(XBASE, WBASE)                                                                  \
+    {                                                                                             \
+        const float4 wa = *reinterpret_cast<const float4*>((WBASE) + 0 * C + tx * 4);             \
+        const float4 wb = *reinterpret_cast<const float4*>((WBASE) + 1 * C + tx * 4);             \
+        const float4 wc = *reinterpret_cast<const float4*>((WBASE) + 2 * C + tx * 4);             \
+        const float4 wd = *reinterpret_cast<const float4*>((WBASE) + 3 * C + tx * 4);             \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) {                                           \
+            const float4 xv = *reinterpret_cast<const float4*>((XBASE) + (size_t)(ty + TY * i) * XS); \
+            acc[i][0] = fmaf(xv.x, wa.x, acc[i][0]); acc[i][1] = fmaf(xv.x, wa.y, acc[i][1]);      \
+            acc[i][2] = fmaf(xv.x, wa.z, acc[i][2]); acc[i][3] = fmaf(xv.x, wa.w, acc[i][3]);      \
+            acc[i][0] = fmaf(xv.y, wb.x, acc[i][0]); acc[i][1] = fmaf(xv.y, wb.y, acc[i][1]);      \
+            acc[i][2] = fmaf(xv.y, wb.z, acc[i][2]); acc[i][3] = fmaf(xv.y, wb.w, acc[i][3]);      \
+            acc[i][0] = fmaf(xv.z, wc.x, acc[i][0]); acc[i][1] = fmaf(xv.z, wc.y, acc[i][1]);      \
+            acc[i][2] = fmaf(xv.z, wc.z, acc[i][2]); acc[i][3] = fmaf(xv.z, wc.w, acc[i][3]);      \
+            acc[i][0] = fmaf(xv.w, wd.x, acc[i][0]); acc[i][1] = fmaf(xv.w, wd.y, acc[i][1]);      \
+            acc[i][2] = fmaf(xv.w, wd.z, acc[i][2]); acc[i][3] = fmaf(xv.w, wd.w, acc[i][3]);      \
+        }                                                                                         \
+    }
+#pragma unroll 1
+    for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll 2
+        for (int k4 = 0; k4 < C / 4; ++k4)
+            JK_RB_STEP(xs + (size_t)tap * TT * XS + k4 * 4, w1s + ((size_t)tap * C + k4 * 4) * C)
+    }
+    {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b1) + tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 h;
+            h.x = fmaxf(acc[i][0] + bv.x, 0.f); h.y = fmaxf(acc[i][1] + bv.y, 0.f);
+            h.z = fmaxf(acc[i][2] + bv.z, 0.f); h.w = fmaxf(acc[i][3] + bv.w, 0.f);
+            *reinterpret_cast<float4*>(hs + (size_t)(ty + TY * i) * XS + tx * 4) = h;
+            acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int k4 = 0; k4 < C / 4; ++k4) JK_RB_STEP(hs + k4 * 4, w2s + (size_t)(k4 * 4) * C)
+#undef JK_RB_STEP
+    {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b2) + tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long t = t0 + ty + TY * i;
+            if (t >= T) continue;
+            const float4 r = __ldg(reinterpret_cast<const float4*>(xin + (size_t)t * C) + tx);
+            float4 v;
+            v.x = rs * (acc[i][0] + bv.x); v.x += r.x;
+            v.y = rs * (acc[i][1] + bv.y); v.y += r.y;
+            v.z = rs * (acc[i][2] + bv.z); v.z += r.z;
+            v.w = rs * (acc[i][3] + bv.w); v.w += r.w;
+            *(reinterpret_cast<float4*>(xout + (size_t)t * C) + tx) = v;
+        }
+    }
+}
+
+template <int C>
+int launch_resblock_fused(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
+                          int n, long long T, int dil, float rs, cudaStream_t stream) {
+    constexpr int TX = C / 4, TY = 256 / TX, TT = TY * 8, XS = C + 4;
+    constexpr size_t smem = (size_t)(4 * C * C + 4 * TT * XS) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        JK_CHECK_CUDA(cudaFuncSetAttribute(resblock_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((T + TT - 1) / TT), (unsigned)n);
+    resblock_fused_kernel<C><<<grid, 256, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs);
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// c_out <= 4 (the decoder's final Conv1d(emb_width -> 1 audio channel, k3), encdec.py:109): one thread per output
+// position, weights in shared memory.  The 64 x 64 tile kernel would spend 63/64 of its FMAs on padding here;
+// this one is a stream over the input (HBM bound).  Same accumulation order as the tile kernel (tap, then channel).
+__global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P) {
+    extern __shared__ float wsm[];                       // [n_taps][c_in][c_out]
+    const int nw = P.n_taps * P.c_in * P.c_out;
+    for (int i = threadIdx.x; i < nw; i += 256) wsm[i] = P.w[i];
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= P.t_out) return;
+    const int nb = blockIdx.y;
+    const float* in = P.in + (size_t)nb * P.t_in * P.c_in;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < P.n_taps; ++tap) {
+        const long long tp = t * P.in_stride + P.tap_off[tap];
+        if (tp < 0 || tp >= P.t_in) continue;            // zero padding: fmaf(0, w, acc) == acc
+        const float* xr = in + (size_t)tp * P.c_in;
+        const float* wr = wsm + (size_t)tap * P.c_in * P.c_out;
+        for (int c = 0; c < P.c_in; c += 4) {
+            float4 v = *reinterpret_cast<const float4*>(xr + c);
+            if (P.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < P.c_out) acc[j] = fmaf(xv[e], wr[(c + e) * P.c_out + j], acc[j]);
+        }
+    }
+    const long long rows_out = P.t_out * P.out_stride;
+    const long long orow = t * P.out_stride + P.out_offset;
+    float* out = P.out + ((size_t)nb * rows_out + orow) * P.c_out;
+    const float* res = P.res ? P.res + ((size_t)nb * rows_out + orow) * P.c_out : nullptr;
+    for (int j = 0; j < P.c_out; ++j) {
+        float v = P.scale * (acc[j] + (P.bias ? P.bias[j] : 0.f));
+        if (res) v += res[j];
+        out[j] = v;
+    }
+}
+
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int c_out, int c_in,
                                         int k, int transposed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,6 +462,12 @@ extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
     for (int i = 0; i < 4; ++i) P.tap_off[i] = a->tap_off[i];
     P.in_stride = a->in_stride; P.out_stride = a->out_stride; P.out_offset = a->out_offset; P.relu_in = a->relu_in;
     P.scale = a->scale;
+    if (a->c_out <= 4 && a->c_in % 4 == 0 && (size_t)a->n_taps * a->c_in * a->c_out * 4 <= 32768) {
+        dim3 g((unsigned)((a->t_out + 255) / 256), (unsigned)a->n);
+        conv1d_cl_narrow_kernel<<<g, 256, (size_t)a->n_taps * a->c_in * a->c_out * 4, stream>>>(P);
+        JK_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((unsigned)((a->t_out + 63) / 64), (unsigned)((a->c_out + 63) / 64), (unsigned)a->n);
     conv1d_cl_kernel<<<grid, 256, 0, stream>>>(P);
     JK_CHECK_CUDA(cudaGetLastError());
@@ -311,7 +477,12 @@ extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
 extern "C" int jk_resblock_cl(const float* x, float* out, float* tmp, const float* w1, const float* b1, const float* w2,
                               const float* b2, int n, int64_t T, int C, int Cs, int dilation, float res_scale,
                               jk_stream_t stream) {
-    JK_REQUIRE(x && out && tmp && w1 && w2, "null argument");
+    JK_REQUIRE(x && out && w1 && w2, "null argument");
+    if (C == Cs && b1 && b2 && x != out && T > 0 && !getenv("JK_NO_FUSED_RESBLOCK")) {   // the VQ-VAE's own shapes: one fused launch
+        if (C == 64) return launch_resblock_fused<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+        if (C == 32) return launch_resblock_fused<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    }
+    JK_REQUIRE(tmp, "tmp ([n, T, Cs] floats) is required for shapes without the fused kernel");
     jk_conv_args a;
     a.in = x; a.t_in = T; a.c_in = C; a.out = tmp; a.t_out = T; a.c_out = Cs; a.w = w1; a.bias = b1; a.res = nullptr;
     a.n_taps = 3; a.tap_off[0] = -dilation; a.tap_off[1] = 0; a.tap_off[2] = dilation; a.tap_off[3] = 0;
