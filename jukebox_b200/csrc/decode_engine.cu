@@ -13,13 +13,13 @@
 //     the order the CTA consumes them, already in mma.sync B-fragment order.  The producer warp
 //     walks that stream with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a
 //     shared-memory ring guarded by full/empty mbarriers.  It is decoupled from the compute
-//     phases, so it keeps prefetching the next GEMMs / next layer (ring ~10 x 16 KB per SM) while
+//     phases, so it keeps prefetching the next GEMMs / next layer (ring 6 x 16 KB per SM) while
 //     the consumers sit in a grid barrier or in the attention phase.
 //   * every Conv1D at decode is [16 x K] x [K x N]: M = 16 is exactly the m16n8k16 tensor-core
 //     tile, so consumers use warp-level mma.sync with fp32 accumulation; each CTA owns 8-column
 //     groups of N and the full K (no cross-CTA split-K, deterministic).  tcgen05 needs M >= 64
 //     and would re-read a 4x zero-padded A tile from shared memory for every 8-16 weight
-//     columns; it is used where tiles are >= 128 rows (prefill GEMM, VQ-VAE).
+//     columns; it is used where tiles are >= 128 rows (chunked prefill: prefill.cu / prefill_gemm.cu).
 //   * LayerNorm is fused into the GEMM's activation staging, bias / quick_gelu / residual adds
 //     into its epilogue; fp16 rounding points follow the reference exactly.
 //   * the layer-to-layer dependency is a grid barrier through one L2 counter.
@@ -49,7 +49,6 @@ constexpr int kLogitRowsPerChunk = 4;
 constexpr int kLogitRowsPerPass = 8;
 constexpr int kMaxSplit = 8;
 constexpr int kProfSlots = 1024;
-constexpr int kBarGroup = 12;           // CTAs per first-level barrier counter
 
 struct StepArgs {
     int n;
@@ -72,7 +71,6 @@ extern __shared__ __align__(1024) uint8_t jk_smem[];
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(jk_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(jk_smem) + kMaxSlots; }
 __device__ __forceinline__ float* sm_stats() { return reinterpret_cast<float*>(jk_smem + 256); }
-__device__ __forceinline__ long long* sm_sacc() { return reinterpret_cast<long long*>(jk_smem + 512); }
 __device__ __forceinline__ uint8_t* sm_uni() { return jk_smem + kHeaderBytes; }
 // The engine descriptor lives in global memory; with the shared-memory carve-out at its maximum there is
 // no L1 to cache it, so every `E->field` was an L2 round trip (~300 cycles) on the dependency chain.
