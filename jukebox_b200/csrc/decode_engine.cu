@@ -40,7 +40,7 @@ using namespace jk;
 namespace {
 
 constexpr int kConsumers = 256;
-constexpr int kThreads = 288;          // 8 consumer warps + 1 producer warp
+constexpr int kThreads = 384;          // 2 consumer warpgroups (8 warps) + 1 producer warpgroup (warp 8 works, 9-11 exit)
 constexpr int kSlotBytes = 16384;
 constexpr int kMaxSlots = 12;
 constexpr int kHeaderBytes = 2048;     // barriers, LN statistics, shared copies of the descriptor / layer records
@@ -420,6 +420,32 @@ __device__ __forceinline__ uint32_t kv_chunk_off(int r, int chunk, int dhp, int 
     return (uint32_t)(r * dhp * 2 + ((chunk ^ (r & swz)) << 4));
 }
 
+// cp.async of rows [0, nr) of K and V into swizzled tiles.  Thread -> (first row, chunk) is fixed, so the
+// loop body is two cp.async and two adds: no per-chunk division (the generic i / nvec form cost 1.4 us of
+// issue time per 47-row tile).
+__device__ __forceinline__ void kv_copy_tile(uint32_t kd, uint32_t vd, const __half* ks, const __half* vs, int nr,
+                                             int dhp, int swz) {
+    const int nvec = dhp >> 3, tid = threadIdx.x;
+    if (nvec <= kConsumers && kConsumers % nvec == 0) {
+        const int rstep = kConsumers / nvec, c = tid % nvec;
+#pragma unroll 2
+        for (int r = tid / nvec; r < nr; r += rstep) {
+            const uint32_t o = kv_chunk_off(r, c, dhp, swz);
+            const size_t g = (size_t)r * dhp + c * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + g));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + g));
+        }
+    } else {
+        for (int i = tid; i < nr * nvec; i += kConsumers) {
+            const int r = i / nvec, c = i - r * nvec;
+            const uint32_t o = kv_chunk_off(r, c, dhp, swz);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + i * 8));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + i * 8));
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __noinline__ void attn_scores(uint32_t kt, int dhp, int swz, int nrb, int nr, uint32_t qh_s, float* sc, float scale2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npair = dhp >> 4;
@@ -444,6 +470,51 @@ __device__ __noinline__ void attn_scores(uint32_t kt, int dhp, int swz, int nrb,
                 const int rlo = warp * 16 + (lane >> 2), rhi = rlo + 8;
                 sc[rlo] = (rlo < nr) ? h2f_round(h2f_round(c0[0] + c1[0]) * scale2) : -INFINITY;
                 sc[rhi] = (rhi < nr) ? h2f_round(h2f_round(c0[2] + c1[2]) * scale2) : -INFINITY;
+            }
+        }
+}
+
+// flash-decoding merge of the ns partials of one (sample, head), run by the CTA that finished last.
+// Own function: its registers must not add to attn_item's (see "Register regime" in DESIGN.md).
+__device__ __noinline__ void attn_merge(int item, int ns, int b, int h) {
+    const EngineDev* E = sm_E();
+    const int tid = threadIdx.x, dh = E->dh, dhp = E->dh_pad, S = E->S;
+        const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
+        const int st = dhp + 2;
+        if (ns <= 4) {
+            // every load of the merge is issued before the first use: ONE L2 round trip instead of three
+            // dependent ones (max pass, sum pass, value pass) on the critical path of the slowest CTAs
+            float m[4], l[4], v0[4], v1[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool on = q < ns;
+                m[q] = on ? __ldcg(p0 + (size_t)q * st) : -INFINITY;
+                l[q] = on ? __ldcg(p0 + (size_t)q * st + 1) : 0.f;
+                v0[q] = (on && tid < dh) ? __ldcg(p0 + (size_t)q * st + 2 + tid) : 0.f;
+                v1[q] = (on && tid + kConsumers < dh) ? __ldcg(p0 + (size_t)q * st + 2 + tid + kConsumers) : 0.f;
+            }
+            float M = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) M = fmaxf(M, m[q]);
+            float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < ns) {
+                    const float w = expf(m[q] - M);
+                    Lsum += l[q] * w; o0 += v0[q] * w; o1 += v1[q] * w;
+                }
+            }
+            if (tid < dh) E->a[(size_t)b * S + h * dh + tid] = __float2half_rn(o0 / Lsum);
+            if (tid + kConsumers < dh) E->a[(size_t)b * S + h * dh + tid + kConsumers] = __float2half_rn(o1 / Lsum);
+        } else {
+            float M = -INFINITY;
+            for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * st));
+            float Lsum = 0.f;
+            for (int q = 0; q < ns; ++q) Lsum += __ldcg(p0 + (size_t)q * st + 1) * expf(__ldcg(p0 + (size_t)q * st) - M);
+            for (int d = tid; d < dh; d += kConsumers) {
+                float o = 0.f;
+                for (int q = 0; q < ns; ++q) o += __ldcg(p0 + (size_t)q * st + 2 + d) * expf(__ldcg(p0 + (size_t)q * st) - M);
+                E->a[(size_t)b * S + h * dh + d] = __float2half_rn(o / Lsum);
             }
         }
 }
@@ -502,16 +573,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     auto issue_tile = [&](int ti) {
         const int r0 = i0 + ti * trows, nr = max(0, min(trows, i1 - r0));
         const uint32_t kd = (ti & 1) ? regB : regA, vd = kd + tileB;
-        const __half* ks = kbase + (size_t)r0 * dhp;
-        const __half* vs = vbase + (size_t)r0 * dhp;
-#pragma unroll 2
-        for (int i = tid; i < nr * nvec; i += kConsumers) {
-            const int r = i / nvec, c = i - r * nvec;
-            const uint32_t o = kv_chunk_off(r, c, dhp, swz);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + i * 8));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + i * 8));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        kv_copy_tile(kd, vd, kbase + (size_t)r0 * dhp, vbase + (size_t)r0 * dhp, nr, dhp, swz);
     };
     const bool use_pre = pre && ntiles == 1;
     if (!use_pre) issue_tile(0);
@@ -650,20 +712,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         if (ticket == (unsigned)(ns - 1)) E->acnt[item] = 0u;
     }
     consumer_sync();
-    if (stats[48] != 0.f) {
-        const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
-        float M = -INFINITY;
-        for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * (dhp + 2)));
-        float Lsum = 0.f;
-        for (int q = 0; q < ns; ++q)
-            Lsum += __ldcg(p0 + (size_t)q * (dhp + 2) + 1) * expf(__ldcg(p0 + (size_t)q * (dhp + 2)) - M);
-        for (int d = tid; d < dh; d += kConsumers) {
-            float o = 0.f;
-            for (int q = 0; q < ns; ++q)
-                o += __ldcg(p0 + (size_t)q * (dhp + 2) + 2 + d) * expf(__ldcg(p0 + (size_t)q * (dhp + 2)) - M);
-            E->a[(size_t)b * S + h * dh + d] = __float2half_rn(o / Lsum);
-        }
-    }
+    if (stats[48] != 0.f) attn_merge(item, ns, b, h);
     consumer_sync();
     STAMP(E, pslot, 6);
 }
@@ -686,17 +735,8 @@ __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, 
     const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
     if (i1 - i0 > RC - 1) return 0;
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
-    const __half* ks = LD.kc + (cbase + G.base + i0) * dhp;
-    const __half* vs = LD.vc + (cbase + G.base + i0) * dhp;
     const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + RC * dhp * 2;
-#pragma unroll 2
-    for (int i = threadIdx.x; i < (i1 - i0) * nvec; i += kConsumers) {
-        const int r = i / nvec, cc = i - r * nvec;
-        const uint32_t o = kv_chunk_off(r, cc, dhp, swz);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + o), "l"(ks + i * 8));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vd + o), "l"(vs + i * 8));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    kv_copy_tile(kd, vd, LD.kc + (cbase + G.base + i0) * dhp, LD.vc + (cbase + G.base + i0) * dhp, i1 - i0, dhp, swz);
     return 1;
 }
 
@@ -866,10 +906,14 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
     __syncthreads();
     const bool do_logits = (A.logits != nullptr) && E->bins > 0;
-    if (warp == 8) {
-        producer_loop(Eg, ring, do_logits, c);
+    // Register reallocation between warpgroups (setmaxnreg, sm_90a+): the block launches with 168 registers per
+    // thread (65536 / 384); the producer warpgroup keeps 40 and hands the rest to the two consumer warpgroups.
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8) producer_loop(Eg, ring, do_logits, c);
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int t = *reinterpret_cast<volatile const int*>(E->t);
     const unsigned epoch0 = *reinterpret_cast<volatile const unsigned*>(E->epoch);
     unsigned nbar = 0;
