@@ -184,15 +184,15 @@ __device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
         uint4 x[16];                                          // 16 independent 16-byte loads in flight
         float gm[8], bt[8];
         if (act) {
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-                x[r] = (r < B) ? ldcg_u4(in + (size_t)r * K + v * 8) : make_uint4(0, 0, 0, 0);
-            if (ln) {
+            if (ln) {      // issued first: their latency overlaps the 16-load batch below
                 *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
                 *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
                 *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
                 *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
             }
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                x[r] = (r < B) ? ldcg_u4(in + (size_t)r * K + v * 8) : make_uint4(0, 0, 0, 0);
         }
         if (ln && v0 == 0) consumer_sync();                  // row statistics are in shared memory (loads in flight)
         if (act) {
