@@ -123,6 +123,24 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned k, int cta,
     consumer_sync();
 }
 
+// The attention -> proj boundary is not a full barrier: proj needs every (sample, head) output, and each of
+// those is completed by exactly one CTA (the unsplit item's owner or the merger of its parts).  Completers add
+// to a counter (release), everybody polls it (acquire): B*H arrivals instead of G on the critical path.
+__device__ __forceinline__ unsigned* attn_done_counter(const EngineDev* E) { return E->bar + 64; }
+__device__ __forceinline__ void attn_done_signal(const EngineDev* E) {      // after a consumer_sync that follows the writes of `a`
+    if (threadIdx.x == 0) red_release_add(attn_done_counter(E), 1u);
+}
+__device__ __forceinline__ void attn_done_wait(const EngineDev* E, unsigned target) {
+    consumer_sync();
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while ((int)(ld_acquire_u32(attn_done_counter(E)) - target) < 0) {
+            if (++spins > (1u << 28)) __trap();
+        }
+    }
+    consumer_sync();
+}
+
 __device__ __forceinline__ float ld_half_cg(const __half* p) {
     return __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))));
 }
@@ -560,6 +578,8 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
                 LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
             }
         }
+        consumer_sync();
+        attn_done_signal(E);
         return;
     }
     STAMP(E, pslot, 0);
@@ -696,6 +716,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     STAMP(E, pslot, 3);
     if (ns == 1) {
         consumer_sync();
+        attn_done_signal(E);
         return;
     }
     // ---- split parts: the partial is published, the last finisher merges (flash-decoding merge) ------
@@ -714,6 +735,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     consumer_sync();
     if (stats[48] != 0.f) attn_merge(item, ns, b, h);
     consumer_sync();
+    if (stats[48] != 0.f) attn_done_signal(E);
     STAMP(E, pslot, 6);
 }
 
@@ -916,7 +938,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int t = *reinterpret_cast<volatile const int*>(E->t);
     const unsigned epoch0 = *reinterpret_cast<volatile const unsigned*>(E->epoch);
-    unsigned nbar = 0;
+    unsigned nbar = 0, nreal = 0, ndone = 0;    // phase index (profiling slots), real grid barriers, attention items
+    const unsigned done0 = *reinterpret_cast<volatile const unsigned*>(E->bar + 1600);
     const int B = A.n, W = E->W, S = E->S, M = E->M, G = E->G;
 #define GRID_BARRIER()                                                                     \
     do {                                                                                   \
@@ -927,7 +950,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             E->prof3[((nbar - 6) * 256 + c) * 2] = now_;                                   \
         }                                                                                  \
         ++nbar;                                                                            \
-        grid_barrier(E->bar, epoch0 + nbar, c, G);                                         \
+        ++nreal;                                                                           \
+        grid_barrier(E->bar, epoch0 + nreal, c, G);                                        \
         if (tid == 0 && E->prof_on && nbar >= 7 && nbar < 12) {                            \
             unsigned long long now_;                                                       \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
@@ -1019,7 +1043,16 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
                 const int s = it % ns, bh = it / ns;
                 attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nbar, pre_ok && it == c);
             }
-            GRID_BARRIER();
+            STAMP(E, (int)nbar, 4);
+            ++nbar;
+            ndone += (unsigned)(B * E->H);
+            attn_done_wait(E, done0 + ndone);
+            STAMP(E, (int)nbar - 1, 5);
+            if (c == 0 && tid == 0 && E->prof_on && nbar < (unsigned)kProfSlots) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                E->prof[nbar] = now;
+            }
         }
         if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
         {
@@ -1058,7 +1091,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (E->prof_on && nbar + 1 < (unsigned)kProfSlots) E->prof[nbar + 1] = now;
         *E->t = t + 1;
-        *E->epoch = epoch0 + nbar;
+        *E->epoch = epoch0 + nreal;
+        *(E->bar + 1600) = done0 + ndone;
     }
 #undef GRID_BARRIER
 }
