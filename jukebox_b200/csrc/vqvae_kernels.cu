@@ -314,6 +314,102 @@ resblock_fused_kernel(const float* __restrict__ x, float* __restrict__ out, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tile conv for the VQ-VAE's wide layers (c_out = 32 or 64, c_in <= 64): the register tiling of the fused
+// ResConv1DBlock kernel applied to one convolution - all taps' weights and (ReLU'd) input tap tiles in shared
+// memory, 8 positions x 4 channels per thread, FMAs in the generic kernel's order (tap, then input channel),
+// so results are bit-identical to conv1d_cl_kernel.  Covers the k4-s2 down / (two-phase) up-sampling convs and
+// the k3 input convs, i.e. everything between the resblocks.
+// ---------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256, 1) conv1d_cl_tile_kernel(ConvP P) {
+    constexpr int TX = CO / 4, TY = 256 / TX, TT = TY * 8;
+    extern __shared__ __align__(16) float csm[];
+    const int CI = P.c_in, XS = CI + 4, NT = P.n_taps;
+    float* ws = csm;                                   // [NT][CI][CO]
+    float* xs = ws + (size_t)NT * CI * CO;             // [NT][TT][XS]
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    const long long t0 = (long long)blockIdx.x * TT;
+    const float* in = P.in + (size_t)blockIdx.y * P.t_in * CI;
+    for (int i = tid; i < NT * CI * CO / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(P.w) + i);
+    const int c4n = CI / 4;
+    for (int tap = 0; tap < NT; ++tap) {
+        const long long off = tap == 0 ? P.tap_off[0] : tap == 1 ? P.tap_off[1] : tap == 2 ? P.tap_off[2] : P.tap_off[3];
+#pragma unroll 4
+        for (int i = tid; i < TT * c4n; i += 256) {
+            const int t = i / c4n, c4 = i - t * c4n;
+            const long long tp = (t0 + t) * P.in_stride + off;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp >= 0 && tp < P.t_in && t0 + t < P.t_out) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)tp * CI) + c4);
+            if (P.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(xs + ((size_t)tap * TT + t) * XS + c4 * 4) = v;
+        }
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < NT; ++tap) {
+        const float* xb = xs + (size_t)tap * TT * XS;
+        const float* wb = ws + (size_t)tap * CI * CO + tx * 4;
+#pragma unroll 2
+        for (int k4 = 0; k4 < c4n; ++k4) {
+            const float4 wa = *reinterpret_cast<const float4*>(wb + (size_t)(k4 * 4 + 0) * CO);
+            const float4 wq = *reinterpret_cast<const float4*>(wb + (size_t)(k4 * 4 + 1) * CO);
+            const float4 wc = *reinterpret_cast<const float4*>(wb + (size_t)(k4 * 4 + 2) * CO);
+            const float4 wd = *reinterpret_cast<const float4*>(wb + (size_t)(k4 * 4 + 3) * CO);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 xv = *reinterpret_cast<const float4*>(xb + (size_t)(ty + TY * i) * XS + k4 * 4);
+                acc[i][0] = fmaf(xv.x, wa.x, acc[i][0]); acc[i][1] = fmaf(xv.x, wa.y, acc[i][1]);
+                acc[i][2] = fmaf(xv.x, wa.z, acc[i][2]); acc[i][3] = fmaf(xv.x, wa.w, acc[i][3]);
+                acc[i][0] = fmaf(xv.y, wq.x, acc[i][0]); acc[i][1] = fmaf(xv.y, wq.y, acc[i][1]);
+                acc[i][2] = fmaf(xv.y, wq.z, acc[i][2]); acc[i][3] = fmaf(xv.y, wq.w, acc[i][3]);
+                acc[i][0] = fmaf(xv.z, wc.x, acc[i][0]); acc[i][1] = fmaf(xv.z, wc.y, acc[i][1]);
+                acc[i][2] = fmaf(xv.z, wc.z, acc[i][2]); acc[i][3] = fmaf(xv.z, wc.w, acc[i][3]);
+                acc[i][0] = fmaf(xv.w, wd.x, acc[i][0]); acc[i][1] = fmaf(xv.w, wd.y, acc[i][1]);
+                acc[i][2] = fmaf(xv.w, wd.z, acc[i][2]); acc[i][3] = fmaf(xv.w, wd.w, acc[i][3]);
+            }
+        }
+    }
+    const long long rows_out = P.t_out * P.out_stride;
+    float* out = P.out + (size_t)blockIdx.y * rows_out * CO;
+    const float* res = P.res ? P.res + (size_t)blockIdx.y * rows_out * CO : nullptr;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.bias) bv = __ldg(reinterpret_cast<const float4*>(P.bias) + tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long t = t0 + ty + TY * i;
+        if (t >= P.t_out) continue;
+        const long long orow = t * P.out_stride + P.out_offset;
+        float4 v;
+        v.x = P.scale * (acc[i][0] + bv.x); v.y = P.scale * (acc[i][1] + bv.y);
+        v.z = P.scale * (acc[i][2] + bv.z); v.w = P.scale * (acc[i][3] + bv.w);
+        if (res) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(res + (size_t)orow * CO) + tx);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        *(reinterpret_cast<float4*>(out + (size_t)orow * CO) + tx) = v;
+    }
+}
+
+template <int CO>
+int launch_conv_tile(const ConvP& P, int n, cudaStream_t stream, bool* took) {
+    constexpr int TX = CO / 4, TY = 256 / TX, TT = TY * 8;
+    const size_t smem = ((size_t)P.n_taps * P.c_in * CO + (size_t)P.n_taps * TT * (P.c_in + 4)) * sizeof(float);
+    *took = false;
+    if (smem > 220 * 1024) return 0;
+    JK_CHECK_CUDA(cudaFuncSetAttribute(conv1d_cl_tile_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    dim3 grid((unsigned)((P.t_out + TT - 1) / TT), (unsigned)n);
+    conv1d_cl_tile_kernel<CO><<<grid, 256, smem, stream>>>(P);
+    JK_CHECK_CUDA(cudaGetLastError());
+    *took = true;
+    return 0;
+}
+
 template <int C>
 int launch_resblock_fused(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
                           int n, long long T, int dil, float rs, cudaStream_t stream) {
@@ -467,6 +563,14 @@ extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
         conv1d_cl_narrow_kernel<<<g, 256, (size_t)a->n_taps * a->c_in * a->c_out * 4, stream>>>(P);
         JK_CHECK_CUDA(cudaGetLastError());
         return 0;
+    }
+    if ((a->c_out == 64 || a->c_out == 32) && a->c_in % 4 == 0 && a->c_in >= 4 && a->c_in <= 64 &&
+        (((uintptr_t)a->in | (uintptr_t)a->out | (uintptr_t)a->w | (uintptr_t)a->bias | (uintptr_t)a->res) & 15) == 0 &&
+        !getenv("JK_NO_TILE_CONV")) {
+        bool took = false;
+        const int rc = a->c_out == 64 ? launch_conv_tile<64>(P, a->n, stream, &took) : launch_conv_tile<32>(P, a->n, stream, &took);
+        if (rc) return rc;
+        if (took) return 0;
     }
     dim3 grid((unsigned)((a->t_out + 63) / 64), (unsigned)((a->c_out + 63) / 64), (unsigned)a->n);
     conv1d_cl_kernel<<<grid, 256, 0, stream>>>(P);
