@@ -184,6 +184,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture of the decode kernel (bytes per
+    launch), or None"""
+    try:
+        tot = 0.0
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 4 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] == "=":
+                tot += float(f[2]) * scale.get(f[3], 1.0)
+        return tot or None
+    except Exception:
+        return None
+
+
 def cpu_baseline(prior_state, cfg, n, tokens, seed=0):
     """oracle (numpy fp32 restatement of the reference's CA2D.sample body) on the host cores"""
     import numpy as np
@@ -471,7 +486,9 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = total_bytes / (kern_ms * 1e-3) / 1e9
-    roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+    traffic = None if args.small else ncu_dram_bytes(os.path.join(ROOT, "profiles", "ncu_decode_step_full_r01.txt"))
+    roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                traffic_source="profiles/ncu_decode_step_full_r01.txt (ncu --set full, one launch at position 4000)",
                 kernel="jk_decode_step_kernel", launches=L, avg_launch_us=1e3 * kern_ms / L,
                 algorithmic_bytes_per_launch=total_bytes / L, weight_bytes_per_launch=w_bytes,
                 peak_source="MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s")
