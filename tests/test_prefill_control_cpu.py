@@ -1,0 +1,76 @@
+"""Host-side control flow of the sampling loop around the engine (no GPU: the engine and the sampling kernel are
+replaced by recorders).  Which positions go through jk_prior_prefill, which through jk_prior_step, and which
+get a token drawn - the bookkeeping of ConditionalAutoregressive2D.primed_sample (reference
+prior/autoregressive.py:251-359)."""
+import torch
+
+import jukebox_b200.prior.autoregressive as ar
+
+
+class FakeEngine:
+    def __init__(self, capacity):
+        self.prefill_capacity = capacity
+        self.calls = []
+        self.position = 0
+
+    def reset(self, t0=0):
+        self.position = t0
+
+    def set_encoder_kv(self, kv):
+        self.calls.append(("enc", tuple(kv.shape)))
+
+    def prefill(self, n, P, **kw):
+        assert self.position == 0
+        self.calls.append(("prefill", n, P))
+        self.position = P
+
+    def step(self, n, tokens=None, logits=None, **kw):
+        self.calls.append(("step", self.position, logits is not None))
+        if logits is not None:
+            logits.zero_()
+        self.position += 1
+
+
+def _model(monkeypatch, capacity):
+    m = ar.ConditionalAutoregressive2D((24,), 16, width=64, depth=2, heads=1, attn_order=0, blocks=None).eval()
+    eng = FakeEngine(capacity)
+    monkeypatch.setattr(m, "_engine", lambda n: eng)
+    monkeypatch.setattr(m.transformer, "check_cache", lambda *a, **k: None)
+    drawn = []
+
+    def fake_sample(logits, temp, seed, position, tokens):
+        drawn.append(position)
+        tokens[:, position] = position % 16
+    monkeypatch.setattr(ar, "sample_categorical", fake_sample)
+    return m, eng, drawn
+
+
+def test_primed_sample_prefills_the_given_tokens_once(monkeypatch):
+    m, eng, drawn = _model(monkeypatch, capacity=512)
+    prime = torch.randint(0, 16, (3, 7))
+    z = m.primed_sample(3, prime, fp16=True, temp=0.9, sample_tokens=12)
+    assert eng.calls[0] == ("prefill", 3, 7)
+    steps = [c for c in eng.calls if c[0] == "step"]
+    assert [c[1] for c in steps] == list(range(7, 12)) and all(c[2] for c in steps)   # every later step wants logits
+    assert drawn == list(range(7, 12))
+    assert torch.equal(z[:, :7], prime) and z.shape == (3, 12)
+
+
+def test_stepping_when_prefill_is_unavailable_or_preds_are_wanted(monkeypatch):
+    for capacity, get_preds in ((0, False), (4, False), (512, True)):
+        m, eng, drawn = _model(monkeypatch, capacity)
+        prime = torch.randint(0, 16, (2, 7))
+        out = m.primed_sample(2, prime, fp16=True, get_preds=get_preds, sample_tokens=10)
+        assert all(c[0] == "step" for c in eng.calls)
+        assert [c[1] for c in eng.calls] == list(range(10))
+        # logits are only requested where something is done with them
+        assert [c[2] for c in eng.calls] == [get_preds or t >= 7 for t in range(10)]
+        assert drawn == [7, 8, 9]
+        if get_preds:
+            assert out[1].shape == (2, 10, 16)
+
+
+def test_ancestral_sampling_never_prefills(monkeypatch):
+    m, eng, drawn = _model(monkeypatch, capacity=512)
+    z = m.sample(2, fp16=True, sample_tokens=5)
+    assert [c[0] for c in eng.calls] == ["step"] * 5 and drawn == list(range(5)) and z.shape == (2, 5)
