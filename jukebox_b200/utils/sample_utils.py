@@ -1,21 +1,34 @@
-"""Window / batch splitting helpers (reference: jukebox/utils/sample_utils.py)."""
+"""Window / batch splitting helpers with the reference's names and results
+(jukebox/utils/sample_utils.py:4-22), used by sample.py to bound the batch per engine call and to lay the
+sliding windows over a level."""
 import torch as t
 
 
+def _chunks(x, size):
+    return t.split(x, size, dim=0)
+
+
 def split_batch(obj, n_samples, split_size):
-    n_passes = (n_samples + split_size - 1) // split_size
-    if isinstance(obj, t.Tensor):
-        return t.split(obj, split_size, dim=0)
-    if isinstance(obj, list):
-        return list(zip(*[t.split(item, split_size, dim=0) for item in obj]))
+    """Split along dim 0 into pieces of at most `split_size`.
+    Tensor -> tuple of tensors; list of tensors -> list of per-piece tuples; None -> one None per piece."""
     if obj is None:
-        return [None] * n_passes
+        pieces = -(-n_samples // split_size)
+        return [None for _ in range(pieces)]
+    if isinstance(obj, t.Tensor):
+        return _chunks(obj, split_size)
+    if isinstance(obj, list):
+        per_item = [_chunks(item, split_size) for item in obj]
+        return [tuple(parts) for parts in zip(*per_item)]
     raise TypeError('Unknown input type')
 
 
 def get_starts(total_length, n_ctx, hop_length):
-    """window starts covering total_length; the last window is pulled back to end exactly at the end"""
-    starts = []
-    for start in range(0, total_length - n_ctx + hop_length, hop_length):
-        starts.append(total_length - n_ctx if start + n_ctx >= total_length else start)
-    return starts
+    """Starts of the windows of length `n_ctx` that cover [0, total_length) with hop `hop_length`; a window that
+    would run past the end is pulled back so that it ends exactly at the end."""
+    last = total_length - n_ctx
+    out = []
+    start = 0
+    while start < last + hop_length:
+        out.append(min(start, last))
+        start += hop_length
+    return out
