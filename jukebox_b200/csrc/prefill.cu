@@ -226,11 +226,13 @@ extern "C" int jk_prior_prefill(jk_prior* p, const jk_prefill_args* a, jk_stream
         JK_CHECK_CUDA(cudaGetLastError());
     }
     const unsigned ln_grid = (unsigned)((rows + 7) / 8);
-    static bool attr_set = false;
+    static bool attr_set[64] = {};         // per device: the attribute belongs to the device's copy of the function
     const size_t fwd_smem = (size_t)(E.dh + P) * 4;
-    if (!attr_set) {
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
         JK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     JK_REQUIRE(fwd_smem <= 64 * 1024, "prefill attention tile too large");
     for (int l = 0; l < c.depth; ++l) {

@@ -415,10 +415,12 @@ int launch_resblock_fused(const float* x, float* out, const float* w1, const flo
                           int n, long long T, int dil, float rs, cudaStream_t stream) {
     constexpr int TX = C / 4, TY = 256 / TX, TT = TY * 8, XS = C + 4;
     constexpr size_t smem = (size_t)(4 * C * C + 4 * TT * XS) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};         // per device: the attribute belongs to the device's copy of the function
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
         JK_CHECK_CUDA(cudaFuncSetAttribute(resblock_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     dim3 grid((unsigned)((T + TT - 1) / TT), (unsigned)n);
     resblock_fused_kernel<C><<<grid, 256, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs);
