@@ -4,27 +4,36 @@
 // (reference: ConditionalAutoregressive2D.sample loop body, prior/autoregressive.py:222-237,
 //  -> Transformer.forward(sample=True), transformer/transformer.py:169-192).
 //
-// Why this shape (DESIGN.md has the numbers): at n_samples <= 16 the step is HBM-bound on
-// weight streaming (83-99 % of the bytes), so the design goal is "every SM streams its private,
-// contiguous slice of every weight matrix exactly once per step, never stalling on the
-// layer-to-layer dependency chain":
-//   * grid = #SMs persistent CTAs (cooperative launch), 8 consumer warps + 1 producer warp
-//   * weights are pre-packed (jk_prior_load_layer) into one contiguous byte stream per CTA, in
-//     the order the CTA consumes them, already in mma.sync B-fragment order.  The producer warp
-//     walks that stream with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a
-//     shared-memory ring guarded by full/empty mbarriers.  It is decoupled from the compute
-//     phases, so it keeps prefetching the next GEMMs / next layer (ring 6 x 16 KB per SM) while
-//     the consumers sit in a grid barrier or in the attention phase.
-//   * every Conv1D at decode is [16 x K] x [K x N]: M = 16 is exactly the m16n8k16 tensor-core
-//     tile, so consumers use warp-level mma.sync with fp32 accumulation; each CTA owns 8-column
-//     groups of N and the full K (no cross-CTA split-K, deterministic).  tcgen05 needs M >= 64
-//     and would re-read a 4x zero-padded A tile from shared memory for every 8-16 weight
-//     columns; it is used where tiles are >= 128 rows (chunked prefill: prefill.cu / prefill_gemm.cu).
-//   * LayerNorm is fused into the GEMM's activation staging, bias / quick_gelu / residual adds
-//     into its epilogue; fp16 rounding points follow the reference exactly.
-//   * the layer-to-layer dependency is a grid barrier through one L2 counter.
-//   * KV caches are laid out per attention pattern so that the rows a token attends are one
-//     contiguous run (transpose-block layers store position p at row (p % bc)*blocks + p / bc).
+// Why this shape (DESIGN.md has the numbers).  At n_samples <= 16 the step is HBM-bound on weight streaming
+// (83-99 % of the bytes) but a 72-layer stack is a chain of 360 dependent phases, each needing what EVERY SM
+// produced in the previous one.  Round 1 paid a grid-wide barrier (1.2-1.7 us) plus a 148-fold redundant
+// activation staging (1-2 us) per phase and sat at 0.14 of the HBM roofline.  This version has NO grid barrier:
+//   * grid = #SMs persistent CTAs (cooperative launch: co-residency), 8 consumer warps + 1 producer warp
+//   * weights are pre-packed (jk_prior_load_layer) into one contiguous byte stream per CTA, in consumption
+//     order, in mma.sync B-fragment order.  The producer warp walks it with 1-D TMA bulk copies
+//     (cp.async.bulk -> SASS UBLKCP) into a shared-memory ring guarded by full/empty mbarriers and runs ahead
+//     of the compute phases by the ring's depth.
+//   * CTAs are grouped in units of KS (4 for 1b_lyrics): a unit owns 8-column groups of every Conv1D, its KS
+//     CTAs split K.  So a CTA stages only K/KS of the activations (and LayerNorms only that), runs
+//     [16 x K/KS] x [K/KS x 8*ncg] on mma.sync m16n8k16, and the KS partial sums meet through an exchange
+//     buffer; each CTA then finishes 1/KS of the unit's columns (bias, quick_gelu / residual, fp16 rounding).
+//   * every producer -> consumer hand-over is an "LL" exchange (NCCL's low-latency protocol): a value travels
+//     as one 8-byte word {data, flag} written by a single store; the consumer polls the word itself.  One
+//     L2 round trip instead of release-counter + acquire-poll + data load, and arrival skew is absorbed word
+//     by word.  Flags are unique per (step, layer), nothing is ever reset.
+//   * LayerNorm statistics need all columns of a row: producers add sum / sum-of-squares of their columns
+//     into 64-bit fixed-point accumulators (exact, order independent) and release-add an arrival counter;
+//     the LN consumers acquire it.  These two all-to-all points per layer are also what makes buffer reuse
+//     safe (see "hazards" below).
+//   * the residual stream never leaves the SM: the CTA that finishes columns c of proj finishes the same
+//     columns of proj2 (and of the embedding), so h / x1 slices live in shared memory.
+//   * KV caches are laid out per attention pattern so that the rows a token attends are one contiguous run
+//     (transpose-block layers store position p at row (p % bc)*blocks + p / bc).
+//
+// Hazards.  A buffer written once per layer may be overwritten for layer l+1 only after every reader of layer
+// l is done.  Every writer first passes an LN statistics wait of layer l+1 (acquire of a counter all G CTAs
+// release-add to AFTER their previous phases, in program order), so all reads of layer l happen-before it.
+// The partial-sum exchange has one buffer per Conv1D index for the same reason.
 //
 // Numerics: activations fp16, accumulation fp32, LayerNorm/softmax fp32 - see oracle/transformer_np.py.
 #include "engine.cuh"
@@ -43,12 +52,13 @@ constexpr int kConsumers = 256;
 constexpr int kThreads = 384;          // 2 consumer warpgroups (8 warps) + 1 producer warpgroup (warp 8 works, 9-11 exit)
 constexpr int kSlotBytes = 16384;
 constexpr int kMaxSlots = 12;
-constexpr int kHeaderBytes = 2048;     // barriers, LN statistics, shared copies of the descriptor / layer records
+constexpr int kHeaderBytes = 8192;     // barriers, LN statistics, descriptor / layer records, residual slice
 constexpr int kLogitKT = 1024;         // K tile (floats) of the fp32 logits product
 constexpr int kLogitRowsPerChunk = 4;
 constexpr int kLogitRowsPerPass = 8;
 constexpr int kMaxSplit = 8;
 constexpr int kProfSlots = 1024;
+constexpr int kXpCols = 64;            // columns per unit in the partial-sum exchange (8 groups of 8)
 
 struct StepArgs {
     int n;
@@ -67,10 +77,14 @@ struct StepArgs {
 // pointers from this symbol (never from pointer parameters): that is what lets the compiler emit
 // LDS/STS/ATOMS instead of generic LD/ST (measured: generic loads of the B fragments made the MMA loop
 // 6x slower than the tensor pipe allows).
+//   [0, 192)      ring mbarriers          [256, 512)    LN row statistics + flags
+//   [512, 1024)   descriptor head         [1024, 1536)  two layer records (+ column assignment at +128)
+//   [2048, 6144)  residual-stream slice of this CTA: [16][32] float2
 extern __shared__ __align__(1024) uint8_t jk_smem[];
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(jk_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(jk_smem) + kMaxSlots; }
 __device__ __forceinline__ float* sm_stats() { return reinterpret_cast<float*>(jk_smem + 256); }
+__device__ __forceinline__ float2* sm_res() { return reinterpret_cast<float2*>(jk_smem + 2048); }
 __device__ __forceinline__ uint8_t* sm_uni() { return jk_smem + kHeaderBytes; }
 // The engine descriptor lives in global memory; with the shared-memory carve-out at its maximum there is
 // no L1 to cache it, so every `E->field` was an L2 round trip (~300 cycles) on the dependency chain.
@@ -105,40 +119,38 @@ __device__ __forceinline__ int kpc_of(int ncg) {
     return k < 8 ? 8 : k;
 }
 
-// Grid-wide barrier through one L2 counter: release-add by one thread after a CTA barrier, acquire
-// polling, CTA barrier.  The CTA barriers make the pattern cumulative for the whole block, no separate
-// membar is needed.  Measured on B200 (tools/micro/ubench.cu): 2320 cycles = 1.18 us for 148 CTAs; a
-// two-level variant (group counters + top counter) measured 1.8-2.3 us in situ (two dependent
-// release/acquire round trips), so the flat counter stays.  `k` = global index of this barrier.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned k, int cta, int G) {
-    consumer_sync();
-    if (threadIdx.x == 0) {
-        red_release_add(bar, 1u);
-        const unsigned target = k * (unsigned)G;
-        unsigned spins = 0;
-        while ((int)(ld_acquire_u32(bar) - target) < 0) {
-            if (++spins > (1u << 28)) __trap();
-        }
-    }
-    consumer_sync();
+// ---- LL words ------------------------------------------------------------------------------
+// 8 bytes = {data (low 32 bits), flag (high 32 bits)}.  A naturally aligned 8-byte access is single-copy
+// atomic, so a reader that sees the flag sees the data; relaxed gpu-scope accesses go to L2 (no L1).
+__device__ __forceinline__ void ll_st(unsigned long long* p, uint32_t data, uint32_t flag) {
+    const unsigned long long v = ((unsigned long long)flag << 32) | data;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-// The attention -> proj boundary is not a full barrier: proj needs every (sample, head) output, and each of
-// those is completed by exactly one CTA (the unsplit item's owner or the merger of its parts).  Completers add
-// to a counter (release), everybody polls it (acquire): B*H arrivals instead of G on the critical path.
-__device__ __forceinline__ unsigned* attn_done_counter(const EngineDev* E) { return E->bar + 64; }
-__device__ __forceinline__ void attn_done_signal(const EngineDev* E) {      // after a consumer_sync that follows the writes of `a`
-    if (threadIdx.x == 0) red_release_add(attn_done_counter(E), 1u);
+__device__ __forceinline__ ulonglong2 ll_ld2(const unsigned long long* p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ void attn_done_wait(const EngineDev* E, unsigned target) {
-    consumer_sync();
-    if (threadIdx.x == 0) {
-        unsigned spins = 0;
-        while ((int)(ld_acquire_u32(attn_done_counter(E)) - target) < 0) {
-            if (++spins > (1u << 28)) __trap();
-        }
-    }
-    consumer_sync();
+__device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool ll_ok(unsigned long long w, uint32_t flag) { return (uint32_t)(w >> 32) == flag; }
+__device__ __forceinline__ void spin_guard(unsigned& spins) {
+    if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
+}
+// one LL word, polled
+__device__ __forceinline__ uint32_t ll_wait1(const unsigned long long* p, uint32_t flag) {
+    unsigned spins = 0;
+    unsigned long long w = ll_ld1(p);
+    while (!ll_ok(w, flag)) { spin_guard(spins); w = ll_ld1(p); }
+    return (uint32_t)w;
+}
+// acquire of an arrival counter (wrap-safe comparison)
+__device__ __forceinline__ void wait_counter(const unsigned* cnt, unsigned target) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire_u32(cnt) - target) < 0) spin_guard(spins);
 }
 
 __device__ __forceinline__ float ld_half_cg(const __half* p) {
@@ -154,10 +166,10 @@ __device__ __forceinline__ float quick_gelu_f(float x) {
 }
 
 // ---------------------------------------------------------------------------------------
-// LayerNorm statistics travel with the activations: whoever WRITES a row block of the residual
+// LayerNorm statistics travel with the activations: whoever WRITES columns of the residual
 // stream also adds sum(x) and sum(x^2) of its columns into per-row 64-bit fixed-point accumulators
 // (exact integer adds => order independent => bit-reproducible), so the consuming GEMM can
-// normalise while it stages - no extra passes over the row, no extra grid barrier.
+// normalise while it stages - no extra passes over the row.
 //   sum  : x * 2^24 is an exact integer for every fp16 value
 //   sumsq: x^2 is exact in fp32; scaled by 2^16 and rounded per element (a pure function of x)
 // ---------------------------------------------------------------------------------------
@@ -167,19 +179,43 @@ __device__ __forceinline__ void red_add_s64(long long* p, long long v) {
     atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
 }
 
-// activation staging: global fp16 [16][K] -> shared fp16 [16][K+8] (ldmatrix friendly), optionally
-// through LayerNorm (fp32 math, eps 1e-5; reference transformer/ops.py:14-24).  Each thread owns 8-column
-// vectors: 8 independent 16-byte loads in flight per batch, raw store, then (LN) a rolled in-place pass
-// over its own vectors.  Loops are deliberately NOT unrolled beyond that: the whole per-layer code must
-// stay inside the 32 KB instruction cache - an earlier fully unrolled build measured ~2.5 us of
-// instruction-fetch stalls in EVERY phase (profiles/ phase_profile_r01d.txt).
-__device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
-                                        const float* gamma, const float* beta, const long long* lnacc) {
+// This CTA's statistics contribution + arrival.  sfx: [2][n_el] fixed-point values of the elements it wrote,
+// element e belongs to row e / ppc.  32 threads each reduce one (row, moment) in a fixed order, one 64-bit red
+// each; then ONE release-add of the arrival counter (the CTA barrier in front makes it cumulative).
+__device__ __forceinline__ void publish_stats(long long* ln_out, unsigned* cnt, int B, int ppc, int n_el) {
+    const int tid = threadIdx.x;
+    consumer_sync();
+    if (ln_out && ppc > 0 && tid < 2 * B) {
+        const long long* sfx = reinterpret_cast<const long long*>(sm_uni() + 32768) + (tid & 1) * 1024;
+        const int row = tid >> 1;
+        long long s = 0;
+        for (int i = 0; i < ppc; ++i) s += sfx[row * ppc + i];
+        red_add_s64(ln_out + 16 * tid, s);
+    }
+    consumer_sync();
+    if (tid == 0) red_release_add(cnt, 1u);
+    (void)n_el;
+}
+
+// activation staging: LL words of rows [0, B), columns [k0, k0 + Ks) -> shared fp16 [16][Ks+8] (ldmatrix
+// friendly), optionally through LayerNorm (fp32 math, eps 1e-5; reference transformer/ops.py:14-24).
+// Threads are laid out [row group][8-column vector]: a thread keeps ONE column vector (gamma / beta loaded
+// once) and walks rows rg, rg + rgc, ...; four rows = eight 16-byte polled loads in flight per batch.
+// Rows >= B are never written: an MMA output row depends only on its own A row, and those outputs are discarded.
+__device__ __noinline__ void stage_acts(const unsigned long long* in, int K, int k0, int Ks, int B, uint32_t flag, int ln,
+                                        const float* gamma, const float* beta, const long long* lnacc,
+                                        const unsigned* cnt, unsigned target) {
     const int tid = threadIdx.x;
     uint8_t* acts = sm_uni();
     float* stats = sm_stats();
-    const int nvec = K >> 3;
-    const int astride = (K + 8) * 2;
+    const int nvec = Ks >> 3;
+    const int astride = (Ks + 8) * 2;
+    if (ln && tid < 32) {
+        // ONE poller per CTA (148 pollers on the counter's L2 line, not 148 x 16); __syncwarp orders its acquire
+        // before the other lanes' loads of the accumulators
+        if (tid == 0) wait_counter(cnt, target);     // every CTA's statistics have arrived
+        __syncwarp();
+    }
     if (ln && tid < 16) {
         float mean = 0.f, rstd = 0.f;
         if (tid < B) {
@@ -195,43 +231,74 @@ __device__ __noinline__ void stage_acts(const __half* in, int K, int B, int ln,
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rstd;
     }
+    const int cw = nvec >= kConsumers ? kConsumers : nvec;           // column vectors covered per pass
+    const int rgc = nvec >= kConsumers ? 1 : kConsumers / nvec;      // row groups
+    const int cv = tid % cw, rg = tid / cw;
+    const int row_words = K >> 1;
+    bool stats_ready = !ln;
 #pragma unroll 1
-    for (int v0 = 0; v0 < nvec; v0 += kConsumers) {          // uniform trip count: the barrier below is CTA-wide
-        const int v = v0 + tid;
-        const bool act = v < nvec;
-        uint4 x[16];                                          // 16 independent 16-byte loads in flight
+    for (int vb = 0; vb < nvec; vb += cw) {
+        const int v = vb + cv;
+        const bool act = (v < nvec) && (rg < rgc);
         float gm[8], bt[8];
-        if (act) {
-            if (ln) {      // issued first: their latency overlaps the 16-load batch below
-                *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-                *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-                *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-                *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-                x[r] = (r < B) ? ldcg_u4(in + (size_t)r * K + v * 8) : make_uint4(0, 0, 0, 0);
+        if (act && ln) {      // issued first: their latency overlaps the polled loads below
+            *reinterpret_cast<float4*>(gm) = __ldg(reinterpret_cast<const float4*>(gamma + k0 + v * 8));
+            *reinterpret_cast<float4*>(gm + 4) = __ldg(reinterpret_cast<const float4*>(gamma + k0 + v * 8 + 4));
+            *reinterpret_cast<float4*>(bt) = __ldg(reinterpret_cast<const float4*>(beta + k0 + v * 8));
+            *reinterpret_cast<float4*>(bt + 4) = __ldg(reinterpret_cast<const float4*>(beta + k0 + v * 8 + 4));
         }
-        if (ln && v0 == 0) consumer_sync();                  // row statistics are in shared memory (loads in flight)
-        if (act) {
-            if (ln) {
+#pragma unroll 1
+        for (int r0 = rg; r0 < 16; r0 += 4 * rgc) {          // uniform trip count per thread group: barrier below
+            ulonglong2 w[4][2];
+            if (act) {
+                unsigned spins = 0;
+                bool again;
+                do {
+                    again = false;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    __half2* hp = reinterpret_cast<__half2*>(&x[r]);
-                    const float rstd = stats[2 * r + 1], nmr = stats[2 * r];     // nmr = -mean * rstd
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + j * rgc;
+                        if (r < B) {
+                            const unsigned long long* src = in + (size_t)r * row_words + ((k0 + v * 8) >> 1);
+                            w[j][0] = ll_ld2(src);
+                            w[j][1] = ll_ld2(src + 2);
+                        }
+                    }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 f = __half22float2(hp[e]);
-                        f.x = fmaf(fmaf(f.x, rstd, nmr), gm[2 * e], bt[2 * e]);
-                        f.y = fmaf(fmaf(f.y, rstd, nmr), gm[2 * e + 1], bt[2 * e + 1]);
-                        hp[e] = __floats2half2_rn(f.x, f.y);
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = r0 + j * rgc;
+                        if (r < B)
+                            again |= !(ll_ok(w[j][0].x, flag) && ll_ok(w[j][0].y, flag) && ll_ok(w[j][1].x, flag) &&
+                                       ll_ok(w[j][1].y, flag));
+                    }
+                    if (again) spin_guard(spins);
+                } while (again);
+            }
+            if (!stats_ready) { consumer_sync(); stats_ready = true; }     // row statistics are in shared memory
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = r0 + j * rgc;
+                    if (r < B) {
+                        uint4 x = make_uint4((uint32_t)w[j][0].x, (uint32_t)w[j][0].y, (uint32_t)w[j][1].x, (uint32_t)w[j][1].y);
+                        if (ln) {
+                            __half2* hp = reinterpret_cast<__half2*>(&x);
+                            const float rstd = stats[2 * r + 1], nmr = stats[2 * r];     // nmr = -mean * rstd
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __half22float2(hp[e]);
+                                f.x = fmaf(fmaf(f.x, rstd, nmr), gm[2 * e], bt[2 * e]);
+                                f.y = fmaf(fmaf(f.y, rstd, nmr), gm[2 * e + 1], bt[2 * e + 1]);
+                                hp[e] = __floats2half2_rn(f.x, f.y);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(acts + r * astride + v * 16) = x;
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) *reinterpret_cast<uint4*>(acts + r * astride + v * 16) = x[r];
         }
     }
+    if (!stats_ready) consumer_sync();
 }
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -243,7 +310,7 @@ __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-// one ring slot worth of k-steps for this warp.  NCG (8-column groups of this CTA) is a template
+// one ring slot worth of k-steps for this warp.  NCG (8-column groups of this unit) is a template
 // parameter: with a run-time count the compiler serialised every LDS -> HMMA pair through one
 // register pair (tools/micro/ubench.cu: 4070 vs 1170 cycles for the K = 2048 loop).
 template <int NCG>
@@ -261,48 +328,51 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[8][4], uint32_t arow, uin
 }
 
 // ---------------------------------------------------------------------------------------
-// one Conv1D at decode: out[b, cols of this CTA] = epilogue( acts[16,K] . Wslice[K, 8*ncg] )
+// one Conv1D at decode.  Unit u owns columns [8*g0, 8*(g0+ncg)); this CTA (rank r of the unit) owns the K slice
+// [r*K/KS, (r+1)*K/KS):  partial[16, 8*ncg] = acts[16, K/KS] . Wslice, exchanged inside the unit, and this CTA
+// finishes column pairs [r*ppc, (r+1)*ppc) of the unit: out = epilogue(sum of the KS partials in rank order).
 // ---------------------------------------------------------------------------------------
 enum { EPI_QKV = 0, EPI_PROJ = 1, EPI_FC = 2, EPI_PROJ2 = 3 };
 
 struct GemmArgs {
-    const __half* in;
+    const unsigned long long* in;       // LL input [16][K/2]
+    unsigned long long* out;            // LL output [16][N/2]
+    unsigned long long* xp;             // partial-sum exchange of this Conv1D index
     int K, N, g0, ncg, ln, epi, pslot;
+    uint32_t flag_in, flag_out;
     const float *gamma, *beta, *bias;
     const long long* ln_in;
-    long long* ln_out;
+    const unsigned* cnt_in;             // arrival counter behind ln_in
+    unsigned target_in;
+    long long* ln_out;                  // statistics of the rows this epilogue writes (residual epilogues)
+    unsigned* cnt_out;                  // arrival counter to add to when done (residual epilogues)
 };
 
 __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
-    if (g.ncg == 0) return ring;
-    const int ncg = g.ncg;
-    STAMP(E, g.pslot, 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int K = g.K, N = g.N, epi = g.epi;
-    const int nc = ncg * 8;
-    const bool residual = (epi == EPI_PROJ || epi == EPI_PROJ2);
-    const __half* res_src = (epi == EPI_PROJ) ? E->h : E->x1;
-    __half* res_dst = (epi == EPI_PROJ) ? E->x1 : E->h;
-    // epilogue operands of this thread's first output element: issue the loads now, use them at the end
-    const bool has_e = tid < B * nc;
-    const int eb = has_e ? tid / nc : 0, ecc = has_e ? tid - eb * nc : 0;
-    float pre_bias = 0.f, pre_res = 0.f;
-    if (has_e) {
-        pre_bias = g.bias[g.g0 * 8 + ecc];
-        if (residual) pre_res = ld_half_cg(res_src + (size_t)eb * N + g.g0 * 8 + ecc);
+    const int KS = E->KS, c = blockIdx.x, rank = c % KS;
+    const int ncg = g.ncg, nc = ncg * 8;
+    const int ppc = (nc >> 1) / KS;                      // column pairs this CTA finishes
+    const bool residual = (g.epi == EPI_PROJ || g.epi == EPI_PROJ2);
+    STAMP(E, g.pslot, 0);
+    if (ncg == 0) {                                      // a unit without columns (tiny models) still arrives
+        if (residual) publish_stats(nullptr, g.cnt_out, B, 0, 0);
+        return ring;
     }
-    stage_acts(g.in, K, B, g.ln, g.gamma, g.beta, g.ln_in);
+    const int K = g.K, N = g.N, epi = g.epi;
+    const int Ks = K / KS, k0 = rank * Ks;
+    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in, g.cnt_in, g.target_in);
     consumer_sync();
     STAMP(E, g.pslot, 1);
 
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-    const int nkk = K >> 4;
+    const int nkk = Ks >> 4;
     const int kpc = kpc_of(ncg);
-    const int astride = (K + 8) * 2;
+    const int astride = (Ks + 8) * 2;
     const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
 #define JK_MMA_LOOP(NCG)                                                                      \
     _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                            \
@@ -327,58 +397,95 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     STAMP(E, g.pslot, 2);
     consumer_sync();                       // everyone is done reading the staged activations
     float* red = reinterpret_cast<float*>(uni);   // [8 warps][ncg][16][8]  (<= 32 KB)
-    float* ov = reinterpret_cast<float*>(uni + 32768);   // [16][64] residual-stream outputs of this CTA
     {
         const int r0 = lane >> 2, c0 = (lane & 3) * 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j < ncg) {
                 float* d = red + ((warp * ncg + j) * 16) * 8;
-                d[r0 * 8 + c0] = acc[j][0];
-                d[r0 * 8 + c0 + 1] = acc[j][1];
-                d[(r0 + 8) * 8 + c0] = acc[j][2];
-                d[(r0 + 8) * 8 + c0 + 1] = acc[j][3];
+                *reinterpret_cast<float2*>(d + r0 * 8 + c0) = make_float2(acc[j][0], acc[j][1]);
+                *reinterpret_cast<float2*>(d + (r0 + 8) * 8 + c0) = make_float2(acc[j][2], acc[j][3]);
             }
         }
     }
     consumer_sync();
+    // ---- the KS partial sums of the unit meet: everyone publishes all of its columns ... -------------------
+    const int npair = nc >> 1;
+    unsigned long long* xp_unit = g.xp + (size_t)(c - rank) * 16 * kXpCols;      // [KS][16][64]
+    if (KS > 1) {
 #pragma unroll 1
-    for (int e = tid; e < B * nc; e += kConsumers) {
-        const int b = e / nc, cc = e - b * nc;
-        const int j = cc >> 3, col = cc & 7;
-        float s = 0.f;
+        for (int e = tid; e < B * npair; e += kConsumers) {
+            const int b = e / npair, pr = e - b * npair;
+            const int j = pr >> 2, col = (pr & 3) * 2;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[((w * ncg + j) * 16 + b) * 8 + col];
-        const int gc = g.g0 * 8 + cc;
-        const bool first = (e == tid);
-        const float y = h2f_round(s + (first ? pre_bias : g.bias[gc]));     // Conv1D output, rounded once to fp16
-        if (epi == EPI_QKV) {
-            E->qkv[(size_t)b * N + gc] = __float2half_rn(y);
-        } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
-            E->g[(size_t)b * N + gc] = __float2half_rn(quick_gelu_f(y));
-        } else {
-            // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
-            const float base = first ? pre_res : ld_half_cg(res_src + (size_t)b * N + gc);
-            const float o = h2f_round(base + y);
-            res_dst[(size_t)b * N + gc] = __float2half_rn(o);
-            ov[b * 64 + cc] = o;
+            for (int w = 0; w < 8; ++w) {
+                const float2 v = *reinterpret_cast<const float2*>(red + ((w * ncg + j) * 16 + b) * 8 + col);
+                s0 += v.x; s1 += v.y;
+            }
+            unsigned long long* dst = xp_unit + ((size_t)rank * 16 + b) * kXpCols + 2 * pr;
+            const unsigned long long w0 = ((unsigned long long)g.flag_in << 32) | __float_as_uint(s0);
+            const unsigned long long w1 = ((unsigned long long)g.flag_in << 32) | __float_as_uint(s1);
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
         }
     }
     STAMP(E, g.pslot, 3);
-    consumer_sync();                       // red region is reused by the next phase's staging
-    if (residual && g.ln_out) {
-        // statistics for the LayerNorm that will read these rows: warp w reduces rows 2w, 2w+1 of this
-        // CTA's columns in a fixed order (exact integer sums), one 64-bit red per row and moment
+    // ---- ... and finishes its own column pairs ----------------------------------------------------------
+    float2* res = sm_res();
+    long long* sfx = reinterpret_cast<long long*>(uni + 32768);      // [2][1024] statistics of the elements written
+    const int n_el = B * ppc;
 #pragma unroll 1
-        for (int r = 2 * warp; r < 2 * warp + 2 && r < B; ++r) {
-            long long s1 = 0, s2 = 0;
-            for (int cc = lane; cc < nc; cc += 32) { const float o = ov[r * 64 + cc]; s1 += fx_sum(o); s2 += fx_sq(o); }
+    for (int e = tid; e < n_el; e += kConsumers) {
+        const int b = e / ppc, pl = e - b * ppc;
+        const int pr = rank * ppc + pl;                 // pair inside the unit
+        const int gc = g.g0 * 8 + 2 * pr;               // global column of the pair
+        const float2 bias = *reinterpret_cast<const float2*>(g.bias + gc);
+        float s0 = 0.f, s1 = 0.f;
+        if (KS == 1) {
+            const int j = pr >> 2, col = (pr & 3) * 2;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-            if (lane == 0) { red_add_s64(g.ln_out + 16 * (2 * r), s1); red_add_s64(g.ln_out + 16 * (2 * r + 1), s2); }
+            for (int w = 0; w < 8; ++w) {
+                const float2 v = *reinterpret_cast<const float2*>(red + ((w * ncg + j) * 16 + b) * 8 + col);
+                s0 += v.x; s1 += v.y;
+            }
+        } else {
+            ulonglong2 v[4];
+            unsigned spins = 0;
+            bool again;
+            do {
+                again = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < KS) v[q] = ll_ld2(xp_unit + ((size_t)q * 16 + b) * kXpCols + 2 * pr);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < KS) again |= !(ll_ok(v[q].x, g.flag_in) && ll_ok(v[q].y, g.flag_in));
+                if (again) spin_guard(spins);
+            } while (again);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < KS) { s0 += __uint_as_float((uint32_t)v[q].x); s1 += __uint_as_float((uint32_t)v[q].y); }
         }
-        consumer_sync();                   // ov is reused
+        const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
+        __half2 o;
+        if (epi == EPI_QKV) {
+            o = __floats2half2_rn(y0, y1);
+        } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
+            o = __floats2half2_rn(quick_gelu_f(y0), quick_gelu_f(y1));
+        } else {
+            // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
+            const float2 base = res[b * 32 + pl];
+            const float o0 = h2f_round(base.x + y0), o1 = h2f_round(base.y + y1);
+            res[b * 32 + pl] = make_float2(o0, o1);
+            o = __floats2half2_rn(o0, o1);
+            sfx[e] = fx_sum(o0) + fx_sum(o1);
+            sfx[1024 + e] = fx_sq(o0) + fx_sq(o1);
+        }
+        ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
     }
+    STAMP(E, g.pslot, 4);
+    if (residual) publish_stats(g.ln_out, g.cnt_out, B, ppc, n_el);
+    else consumer_sync();                  // red region is reused by the next phase
     return ring;
 }
 
@@ -420,7 +527,7 @@ __device__ __host__ __forceinline__ int attn_tile_rows(int dhp) {
 // how many CTAs share one (sample, head): as few as keep every part inside ONE shared-memory tile
 // (RC - 1 cached rows + the current token's row), bounded by the grid
 __device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache) {
-    const int cap = attn_tile_rows(E->dh_pad) - 1;
+    const int cap = E->RC - 1;
     int ns = (ncache + cap - 1) / cap;
     ns = min(ns, E->G / (B * E->H));
     return max(1, min(kMaxSplit, ns));
@@ -467,90 +574,101 @@ __device__ __forceinline__ void kv_copy_tile(uint32_t kd, uint32_t vd, const __h
 __device__ __noinline__ void attn_scores(uint32_t kt, int dhp, int swz, int nrb, int nr, uint32_t qh_s, float* sc, float scale2) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npair = dhp >> 4;
-        if (warp < nrb) {
-            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            const int mi = lane >> 3;
-            const int arow_i = warp * 16 + (lane & 7) + ((mi & 1) << 3);
-            const uint32_t arow = kt + arow_i * dhp * 2;
-            const int axor = arow_i & swz, ahi = mi >> 1;
+    if (warp < nrb) {
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int mi = lane >> 3;
+        const int arow_i = warp * 16 + (lane & 7) + ((mi & 1) << 3);
+        const uint32_t arow = kt + arow_i * dhp * 2;
+        const int axor = arow_i & swz, ahi = mi >> 1;
 #pragma unroll 2
-            for (int ks = 0; ks < npair; ++ks) {
-                uint32_t a[4];
-                ldsm4(a, arow + (((2 * ks + ahi) ^ axor) << 4));
-                uint32_t b0 = 0u, b1 = 0u;
-                if (lane < 4) {
-                    asm("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(qh_s + (ks * 16 + 2 * lane) * 2));
-                    asm("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(qh_s + (ks * 16 + 8 + 2 * lane) * 2));
-                }
-                if (ks & 1) mma_16816(c1, a, b0, b1); else mma_16816(c0, a, b0, b1);
+        for (int ks = 0; ks < npair; ++ks) {
+            uint32_t a[4];
+            ldsm4(a, arow + (((2 * ks + ahi) ^ axor) << 4));
+            uint32_t b0 = 0u, b1 = 0u;
+            if (lane < 4) {
+                asm("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(qh_s + (ks * 16 + 2 * lane) * 2));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(qh_s + (ks * 16 + 8 + 2 * lane) * 2));
             }
-            if ((lane & 3) == 0) {
-                const int rlo = warp * 16 + (lane >> 2), rhi = rlo + 8;
-                sc[rlo] = (rlo < nr) ? h2f_round(h2f_round(c0[0] + c1[0]) * scale2) : -INFINITY;
-                sc[rhi] = (rhi < nr) ? h2f_round(h2f_round(c0[2] + c1[2]) * scale2) : -INFINITY;
-            }
+            if (ks & 1) mma_16816(c1, a, b0, b1); else mma_16816(c0, a, b0, b1);
         }
+        if ((lane & 3) == 0) {
+            const int rlo = warp * 16 + (lane >> 2), rhi = rlo + 8;
+            sc[rlo] = (rlo < nr) ? h2f_round(h2f_round(c0[0] + c1[0]) * scale2) : -INFINITY;
+            sc[rhi] = (rhi < nr) ? h2f_round(h2f_round(c0[2] + c1[2]) * scale2) : -INFINITY;
+        }
+    }
+}
+
+// attention output of one (sample, head): dims d, d+1 as one LL word of the `a` buffer
+__device__ __forceinline__ void attn_out_pair(const EngineDev* E, int b, int h, int d, float v0, float v1, uint32_t flag) {
+    const __half2 o = __floats2half2_rn(v0, v1);
+    ll_st(E->ll_a + (((size_t)b * E->S + h * E->dh + d) >> 1), *reinterpret_cast<const uint32_t*>(&o), flag);
 }
 
 // flash-decoding merge of the ns partials of one (sample, head), run by the CTA that finished last.
 // Own function: its registers must not add to attn_item's (see "Register regime" in DESIGN.md).
-__device__ __noinline__ void attn_merge(int item, int ns, int b, int h) {
+__device__ __noinline__ void attn_merge(int item, int ns, int b, int h, uint32_t flag) {
     const EngineDev* E = sm_E();
-    const int tid = threadIdx.x, dh = E->dh, dhp = E->dh_pad, S = E->S;
-        const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
-        const int st = dhp + 2;
-        if (ns <= 4) {
-            // every load of the merge is issued before the first use: ONE L2 round trip instead of three
-            // dependent ones (max pass, sum pass, value pass) on the critical path of the slowest CTAs
-            float m[4], l[4], v0[4], v1[4];
+    const int tid = threadIdx.x, dh = E->dh, dhp = E->dh_pad;
+    const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
+    const int st = dhp + 2;
+    const int d = 2 * tid;                  // dims d, d+1 (dh is even, dh <= 512)
+    if (ns <= 4) {
+        // every load of the merge is issued before the first use: ONE L2 round trip instead of three
+        // dependent ones (max pass, sum pass, value pass) on the critical path of the slowest CTAs
+        float m[4], l[4];
+        float2 v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool on = q < ns;
-                m[q] = on ? __ldcg(p0 + (size_t)q * st) : -INFINITY;
-                l[q] = on ? __ldcg(p0 + (size_t)q * st + 1) : 0.f;
-                v0[q] = (on && tid < dh) ? __ldcg(p0 + (size_t)q * st + 2 + tid) : 0.f;
-                v1[q] = (on && tid + kConsumers < dh) ? __ldcg(p0 + (size_t)q * st + 2 + tid + kConsumers) : 0.f;
-            }
-            float M = -INFINITY;
+        for (int q = 0; q < 4; ++q) {
+            const bool on = q < ns;
+            m[q] = on ? __ldcg(p0 + (size_t)q * st) : -INFINITY;
+            l[q] = on ? __ldcg(p0 + (size_t)q * st + 1) : 0.f;
+            v[q] = (on && d < dh) ? __ldcg(reinterpret_cast<const float2*>(p0 + (size_t)q * st + 2 + d)) : make_float2(0.f, 0.f);
+        }
+        float M = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) M = fmaxf(M, m[q]);
-            float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
+        for (int q = 0; q < 4; ++q) M = fmaxf(M, m[q]);
+        float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q < ns) {
-                    const float w = expf(m[q] - M);
-                    Lsum += l[q] * w; o0 += v0[q] * w; o1 += v1[q] * w;
-                }
-            }
-            if (tid < dh) E->a[(size_t)b * S + h * dh + tid] = __float2half_rn(o0 / Lsum);
-            if (tid + kConsumers < dh) E->a[(size_t)b * S + h * dh + tid + kConsumers] = __float2half_rn(o1 / Lsum);
-        } else {
-            float M = -INFINITY;
-            for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * st));
-            float Lsum = 0.f;
-            for (int q = 0; q < ns; ++q) Lsum += __ldcg(p0 + (size_t)q * st + 1) * expf(__ldcg(p0 + (size_t)q * st) - M);
-            for (int d = tid; d < dh; d += kConsumers) {
-                float o = 0.f;
-                for (int q = 0; q < ns; ++q) o += __ldcg(p0 + (size_t)q * st + 2 + d) * expf(__ldcg(p0 + (size_t)q * st) - M);
-                E->a[(size_t)b * S + h * dh + d] = __float2half_rn(o / Lsum);
+        for (int q = 0; q < 4; ++q) {
+            if (q < ns) {
+                const float w = expf(m[q] - M);
+                Lsum += l[q] * w; o0 += v[q].x * w; o1 += v[q].y * w;
             }
         }
+        if (d < dh) attn_out_pair(E, b, h, d, o0 / Lsum, o1 / Lsum, flag);
+    } else {
+        float M = -INFINITY;
+        for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * st));
+        float Lsum = 0.f;
+        for (int q = 0; q < ns; ++q) Lsum += __ldcg(p0 + (size_t)q * st + 1) * expf(__ldcg(p0 + (size_t)q * st) - M);
+        if (d < dh) {
+            float o0 = 0.f, o1 = 0.f;
+            for (int q = 0; q < ns; ++q) {
+                const float w = expf(__ldcg(p0 + (size_t)q * st) - M);
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(p0 + (size_t)q * st + 2 + d));
+                o0 += v.x * w; o1 += v.y * w;
+            }
+            attn_out_pair(E, b, h, d, o0 / Lsum, o1 / Lsum, flag);
+        }
+    }
 }
 
 // One (sample, head, part) work item; q_len == 1 (reference factored_attention.py:82-133 and the
 // per-pattern sample branches :135-228).
-//   * the part's K and V rows are staged with cp.async into swizzled tiles; a part that fits one tile
-//     (RC-1 cached rows + the current token) is ONE tile - and may have been prefetched before the QKV
-//     GEMM - longer parts (dense / prime / enc-dec layers) run double-buffered through both tile regions
+//   * q and the current token's k, v come from the QKV Conv1D as LL words (polled: this is the QKV -> attention
+//     hand-over); the part's cached K and V rows are staged with cp.async into swizzled tiles, issued BEFORE the
+//     poll so their HBM latency overlaps it; a part that fits one tile (RC-1 cached rows + the current token) is
+//     ONE tile, longer parts (dense / prime / enc-dec layers) run double-buffered through both tile regions
 //   * scores on the tensor cores: A = 16 key rows x 16 dims (ldmatrix), B = q in column 0, fp32
 //     accumulate; s = fp16(fp16(q.k) * dh^-1/2) exactly as the reference rounds it
 //   * softmax is flash-style in fp32 (running max / sum), every warp redundantly; P rounded to fp16 as
 //     the reference's w.half(), P.V on the tensor cores (A = P in row 0, B = V via ldmatrix.trans), each
 //     warp owning 16-dim output slices
-//   * parts of one (sample, head) are merged by the last CTA to finish (atomic ticket), so the phase
-//     needs no extra grid barrier
+//   * parts of one (sample, head) are merged by the last CTA to finish (atomic ticket); the output goes to
+//     the `a` LL buffer, which IS the attention -> proj hand-over
 __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int s, int ns,
-                                       const AttnGeom G, int pslot, int pre) {
+                                       const AttnGeom G, int pslot, uint32_t flag) {
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     float* stats = sm_stats();
@@ -559,31 +677,19 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     const int dh = E->dh, dhp = E->dh_pad, S = E->S;
     const int nvec = dhp >> 3, npair = dhp >> 4;
     const int swz = (nvec & 7) ? 0 : 7;
-    const int RC = attn_tile_rows(dhp);
+    const int RC = E->RC;
     const int tileB = RC * dhp * 2;
     const uint32_t regA = smem_u32(uni), regB = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes);
-    __half* qh = reinterpret_cast<__half*>(uni + 2 * tileB);          // [dhp]
-    float* sc = reinterpret_cast<float*>(uni + 2 * tileB + dhp * 2);  // [64] scores of the tile
-    const int qkv_stride = (LD.attn_func == 6) ? S : 3 * S;
-    const __half* qrow = E->qkv + (size_t)b * qkv_stride + h * dh;
+    __half* qh = reinterpret_cast<__half*>(uni + 2 * tileB);          // [dhp] q, then [dhp] k_new, [dhp] v_new
+    __half* kn = qh + dhp;
+    __half* vn = kn + dhp;
+    float* sc = reinterpret_cast<float*>(uni + 2 * tileB + 3 * dhp * 2);  // [64] scores of the tile
+    const int qkv_words = ((LD.attn_func == 6) ? S : 3 * S) >> 1;
+    const unsigned long long* qrow = E->ll_qkv + (size_t)b * qkv_words + ((h * dh) >> 1);
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
     const bool last_part = (s == ns - 1);
     const int R = G.R;
-
-    if (R == 0) {   // prev-block attention inside the first block: keys/values are zeros -> output 0
-        for (int d = tid; d < dh; d += kConsumers) {
-            E->a[(size_t)b * S + h * dh + d] = __float2half_rn(0.f);
-            if (G.wrow >= 0) {
-                LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + S + d));
-                LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
-            }
-        }
-        consumer_sync();
-        attn_done_signal(E);
-        return;
-    }
-    STAMP(E, pslot, 0);
-    const int ncache = R - (G.cur ? 1 : 0);               // rows that come from the cache
+    const int ncache = R - ((R > 0 && G.cur) ? 1 : 0);               // rows that come from the cache
     const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
     const __half* kbase = LD.kc + (cbase + G.base) * dhp;
     const __half* vbase = LD.vc + (cbase + G.base) * dhp;
@@ -595,14 +701,29 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         const uint32_t kd = (ti & 1) ? regB : regA, vd = kd + tileB;
         kv_copy_tile(kd, vd, kbase + (size_t)r0 * dhp, vbase + (size_t)r0 * dhp, nr, dhp, swz);
     };
-    const bool use_pre = pre && ntiles == 1;
-    if (!use_pre) issue_tile(0);
-    for (int d = tid; d < dhp; d += kConsumers) qh[d] = (d < dh) ? __float2half_rn(ld_half_cg(qrow + d)) : __float2half_rn(0.f);
-    if (!G.cur && G.wrow >= 0 && last_part) {   // patterns that do not attend the current token still cache it
-        for (int d = tid; d < dh; d += kConsumers) {
-            LD.kc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + S + d));
-            LD.vc[(cbase + G.wrow) * dhp + d] = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
+    STAMP(E, pslot, 0);
+    if (R > 0) issue_tile(0);               // cached rows do not depend on the current token: load them first
+    // ---- q, k_new, v_new of this (sample, head): LL words of the QKV Conv1D, polled --------------------------
+    {
+        const int hw = dhp >> 1, dw = dh >> 1;
+        const int nsel = (LD.attn_func == 6) ? 1 : 3;
+        for (int i = tid; i < nsel * hw; i += kConsumers) {
+            const int sel = i / hw, wd = i - sel * hw;
+            uint32_t v = 0u;
+            if (wd < dw) v = ll_wait1(qrow + (size_t)sel * (S >> 1) + wd, flag);
+            reinterpret_cast<uint32_t*>(qh)[sel * hw + wd] = v;
         }
+    }
+    consumer_sync();
+    if (G.wrow >= 0 && last_part) {          // cache the current token's k, v
+        for (int i = tid; i < dh; i += kConsumers) {
+            LD.kc[(cbase + G.wrow) * dhp + i] = kn[i];
+            LD.vc[(cbase + G.wrow) * dhp + i] = vn[i];
+        }
+    }
+    if (R == 0) {   // prev-block attention inside the first block: keys/values are zeros -> output 0
+        if (2 * tid < dh) attn_out_pair(E, b, h, 2 * tid, 0.f, 0.f, flag);
+        return;
     }
 
     float m_run = -INFINITY, l_run = 0.f;
@@ -618,21 +739,13 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         }
         const int r0 = i0 + ti * trows;
         int nr = max(0, min(trows, i1 - r0));
-        const uint32_t kt = (use_pre || (ti & 1)) ? regB : regA, vt = kt + tileB;
+        const uint32_t kt = (ti & 1) ? regB : regA, vt = kt + tileB;
         if (ti == ntiles - 1 && last_part && G.cur) {       // append the current token's k, v (from the QKV GEMM)
-            for (int d = tid; d < dhp; d += kConsumers) {
-                __half kh = __float2half_rn(0.f), vh = kh;
-                if (d < dh) {
-                    kh = __float2half_rn(ld_half_cg(qrow + S + d));
-                    vh = __float2half_rn(ld_half_cg(qrow + 2 * S + d));
-                    if (G.wrow >= 0) {
-                        LD.kc[(cbase + G.wrow) * dhp + d] = kh;
-                        LD.vc[(cbase + G.wrow) * dhp + d] = vh;
-                    }
-                }
-                const uint32_t o = kv_chunk_off(nr, d >> 3, dhp, swz) + (d & 7) * 2;
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(kt + o), "h"(__half_as_ushort(kh)));
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(vt + o), "h"(__half_as_ushort(vh)));
+            for (int c8 = tid; c8 < nvec; c8 += kConsumers) {
+                const uint32_t o = kv_chunk_off(nr, c8, dhp, swz);
+                const uint4 kq = *reinterpret_cast<const uint4*>(kn + c8 * 8), vq = *reinterpret_cast<const uint4*>(vn + c8 * 8);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kt + o), "r"(kq.x), "r"(kq.y), "r"(kq.z), "r"(kq.w));
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(vt + o), "r"(vq.x), "r"(vq.y), "r"(vq.z), "r"(vq.w));
             }
             nr += 1;
         }
@@ -698,11 +811,8 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
                         *reinterpret_cast<float2*>(osm + d + 8) = r1;
                     } else if (ns == 1) {
                         const float inv = 1.f / l_run;
-                        __half* ao = E->a + (size_t)b * S + h * dh;
-                        if (d < dh) ao[d] = __float2half_rn(r0.x * inv);
-                        if (d + 1 < dh) ao[d + 1] = __float2half_rn(r0.y * inv);
-                        if (d + 8 < dh) ao[d + 8] = __float2half_rn(r1.x * inv);
-                        if (d + 9 < dh) ao[d + 9] = __float2half_rn(r1.y * inv);
+                        if (d < dh) attn_out_pair(E, b, h, d, r0.x * inv, r0.y * inv, flag);
+                        if (d + 8 < dh) attn_out_pair(E, b, h, d + 8, r1.x * inv, r1.y * inv, flag);
                     } else {
                         float* part = E->part + ((size_t)((b * E->H + h) * kMaxSplit + s)) * (dhp + 2) + 2;
                         *reinterpret_cast<float2*>(part + d) = r0;
@@ -714,11 +824,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         if (ti + 1 < ntiles) consumer_sync();                 // tile buffers and sc are reused
     }
     STAMP(E, pslot, 3);
-    if (ns == 1) {
-        consumer_sync();
-        attn_done_signal(E);
-        return;
-    }
+    if (ns == 1) return;
     // ---- split parts: the partial is published, the last finisher merges (flash-decoding merge) ------
     const int item = b * E->H + h;
     if (tid == 0) {
@@ -733,33 +839,8 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         if (ticket == (unsigned)(ns - 1)) E->acnt[item] = 0u;
     }
     consumer_sync();
-    if (stats[48] != 0.f) attn_merge(item, ns, b, h);
-    consumer_sync();
-    if (stats[48] != 0.f) attn_done_signal(E);
+    if (stats[48] != 0.f) attn_merge(item, ns, b, h, flag);
     STAMP(E, pslot, 6);
-}
-
-// Prefetch of the cached K/V rows of this CTA's first attention work item, issued BEFORE the QKV GEMM of
-// the layer: cached rows do not depend on the current token, so their HBM latency hides behind the
-// whole QKV phase and its barrier.  Only single-tile parts are prefetched; returns 1 if so.
-__device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t) {
-    const EngineDev* E = sm_E();
-    if (!E->kv_prefetch) return 0;
-    const LayerDev LD = LD_ref;
-    const AttnGeom G = attn_geom(E, LD, t);
-    if (G.R == 0) return 0;
-    const int ncache = G.R - (G.cur ? 1 : 0);
-    const int ns = attn_nsplit(E, B, ncache);
-    if (c >= B * E->H * ns) return 0;
-    const int s = c % ns, bh = c / ns, b = bh / E->H, h = bh % E->H;
-    const int dhp = E->dh_pad, nvec = dhp >> 3, RC = attn_tile_rows(dhp);
-    const int swz = (nvec & 7) ? 0 : 7;
-    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
-    if (i1 - i0 > RC - 1) return 0;
-    const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
-    const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + RC * dhp * 2;
-    kv_copy_tile(kd, vd, LD.kc + (cbase + G.base + i0) * dhp, LD.vc + (cbase + G.base + i0) * dhp, i1 - i0, dhp, swz);
-    return 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -767,10 +848,11 @@ __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, 
 // ---------------------------------------------------------------------------------------
 __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int c) {
     if ((threadIdx.x & 31) != 0) return;
-    const uint8_t* src = E->streams + (size_t)c * E->stream_stride + (size_t)E->soff[(size_t)c * (E->depth + 1)] * 16;
+    const uint8_t* src = E->streams + (size_t)c * E->stream_stride;
+    const int KS = E->KS, u = c / KS;
     for (int l = 0; l < E->depth; ++l) {
-        const ushort2* cl = E->cols + ((size_t)c * E->depth + l) * 4;
-        const int Ks[4] = {E->W, E->S, E->W, E->M};
+        const ushort2* cl = E->cols + ((size_t)u * E->depth + l) * 4;
+        const int Ks[4] = {E->W / KS, E->S / KS, E->W / KS, E->M / KS};
         if (c == (l % E->G)) {
             // biases + LayerNorm parameters of this layer (one contiguous block, ~57 KB for 1b_lyrics) are
             // shared by every CTA and evicted from L2 between steps: pull them into L2 ahead of the consumers
@@ -817,7 +899,7 @@ __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool d
 
 // fp32 logits: logits[b, r] = sum_k y[b, k] * x_out[r, k],  y = float(h) (+ cond)
 // (reference autoregressive.py:226-229: fp32 nn.Linear on the fp32 transformer output)
-__device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref, int c, int t) {
+__device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref, int c, int t, uint32_t flag) {
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     const StepArgs A = A_ref;
@@ -834,33 +916,43 @@ __device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref,
         for (int k0 = 0; k0 < W; k0 += kLogitKT) {
             const int kt = min(kLogitKT, W - k0);
             consumer_sync();
-            {   // y = float(h) (+ cond): 8 halves per thread-iteration, loads batched 4 deep
-                const int nv = kt >> 3;
+            {   // y = float(h) (+ cond): the final residual stream as LL words, 4 halves per 16-byte polled load
+                const int nv = kt >> 2;
                 for (int idx0 = tid; idx0 < 16 * nv; idx0 += 4 * kConsumers) {
-                    uint4 hv[4];
+                    ulonglong2 hv[4];
+                    unsigned spins = 0;
+                    bool again;
+                    do {
+                        again = false;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int idx = idx0 + u * kConsumers;
-                        const int b = idx / nv, v = idx - b * nv;
-                        hv[u] = (idx < 16 * nv && b < B) ? ldcg_u4(E->h + (size_t)b * W + k0 + v * 8) : make_uint4(0, 0, 0, 0);
-                    }
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = idx0 + u * kConsumers;
+                            const int b = idx / nv, v = idx - b * nv;
+                            if (idx < 16 * nv && b < B) {
+                                hv[u] = ll_ld2(E->ll_h + (((size_t)b * W + k0 + v * 4) >> 1));
+                                again |= !(ll_ok(hv[u].x, flag) && ll_ok(hv[u].y, flag));
+                            }
+                        }
+                        if (again) spin_guard(spins);
+                    } while (again);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int idx = idx0 + u * kConsumers;
                         if (idx >= 16 * nv) continue;
                         const int b = idx / nv, v = idx - b * nv;
-                        const __half2* hp = reinterpret_cast<const __half2*>(&hv[u]);
-                        float y[8];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { float2 f = __half22float2(hp[e]); y[2 * e] = f.x; y[2 * e + 1] = f.y; }
-                        if (b < B && E->add_cond_after && A.x_cond) {
-                            const float* cp = A.x_cond + ((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + k0 + v * 8;
-                            const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
-                            y[0] += c0.x; y[1] += c0.y; y[2] += c0.z; y[3] += c0.w;
-                            y[4] += c1.x; y[5] += c1.y; y[6] += c1.z; y[7] += c1.w;
+                        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (b < B) {
+                            const uint32_t lo = (uint32_t)hv[u].x, hi = (uint32_t)hv[u].y;
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                            y = make_float4(f0.x, f0.y, f1.x, f1.y);
+                            if (E->add_cond_after && A.x_cond) {
+                                const float* cp = A.x_cond + ((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + k0 + v * 4;
+                                const float4 c0 = *reinterpret_cast<const float4*>(cp);
+                                y.x += c0.x; y.y += c0.y; y.z += c0.z; y.w += c0.w;
+                            }
                         }
-                        *reinterpret_cast<float4*>(ys + b * kt + v * 8) = make_float4(y[0], y[1], y[2], y[3]);
-                        *reinterpret_cast<float4*>(ys + b * kt + v * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                        *reinterpret_cast<float4*>(ys + b * kt + v * 4) = y;
                     }
                 }
             }
@@ -910,16 +1002,17 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     const int tid = threadIdx.x, warp = tid >> 5;
     const int c = blockIdx.x;
     static_assert(offsetof(EngineDev, layer) <= 512, "descriptor head must fit its shared-memory slot");
-    static_assert(sizeof(LayerDev) <= 256, "layer record must fit its shared-memory slot");
+    static_assert(sizeof(LayerDev) <= 128, "layer record must fit its shared-memory slot");
     for (int i = tid; i < (int)(offsetof(EngineDev, layer) / 4); i += kThreads)
         reinterpret_cast<uint32_t*>(jk_smem + 512)[i] = reinterpret_cast<const uint32_t*>(Eg)[i];
     if (tid < (int)(sizeof(LayerDev) / 4))
         reinterpret_cast<uint32_t*>(jk_smem + 1024)[tid] = reinterpret_cast<const uint32_t*>(&Eg->layer[0])[tid];
-    if (tid >= 32 && tid < 36)
-        reinterpret_cast<uint32_t*>(jk_smem + 1024 + 128)[tid - 32] =
-            reinterpret_cast<const uint32_t*>(Eg->cols + ((size_t)c * Eg->depth + 0) * 4)[tid - 32];
     __syncthreads();
     const EngineDev* E = sm_E();
+    const int KS = E->KS, unit = c / KS, rank = c % KS;
+    if (tid >= 32 && tid < 36)
+        reinterpret_cast<uint32_t*>(jk_smem + 1024 + 128)[tid - 32] =
+            reinterpret_cast<const uint32_t*>(E->cols + ((size_t)unit * E->depth + 0) * 4)[tid - 32];
     Ring ring;
     ring.base_off = kHeaderBytes + E->uni_bytes + E->kvpre_bytes; ring.nslot = E->nslot; ring.slot = 0; ring.phase = 0;
     if (tid == 0) {
@@ -937,32 +1030,32 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int t = *reinterpret_cast<volatile const int*>(E->t);
-    const unsigned epoch0 = *reinterpret_cast<volatile const unsigned*>(E->epoch);
-    unsigned nbar = 0, nreal = 0, ndone = 0;    // phase index (profiling slots), real grid barriers, attention items
-    const unsigned done0 = *reinterpret_cast<volatile const unsigned*>(E->bar + 1600);
-    const int B = A.n, W = E->W, S = E->S, M = E->M, G = E->G;
-#define GRID_BARRIER()                                                                     \
-    do {                                                                                   \
-        STAMP(E, (int)nbar, 4);                                                            \
-        if (tid == 0 && E->prof_on && nbar >= 6 && nbar < 11) {                            \
-            unsigned long long now_;                                                       \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
-            E->prof3[((nbar - 6) * 256 + c) * 2] = now_;                                   \
-        }                                                                                  \
-        ++nbar;                                                                            \
-        ++nreal;                                                                           \
-        grid_barrier(E->bar, epoch0 + nreal, c, G);                                        \
-        if (tid == 0 && E->prof_on && nbar >= 7 && nbar < 12) {                            \
-            unsigned long long now_;                                                       \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                       \
-            E->prof3[((nbar - 7) * 256 + c) * 2 + 1] = now_;                               \
-        }                                                                                  \
-        STAMP(E, (int)nbar - 1, 5);                                                        \
-        if (c == 0 && tid == 0 && E->prof_on && nbar < (unsigned)kProfSlots) {             \
-            unsigned long long now;                                                        \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));                        \
-            E->prof[nbar] = now;                                                           \
-        }                                                                                  \
+    // steps executed so far: written only at the very end of a launch by CTA 0, after every CTA of that launch has
+    // passed an all-to-all point - so every CTA of this launch reads the same value
+    const unsigned step = *reinterpret_cast<volatile const unsigned*>(E->sync + 64);
+    const int B = A.n, W = E->W, S = E->S, M = E->M, G = E->G, depth = E->depth;
+    const uint32_t fbase = step * (uint32_t)(depth + 2);          // LL flags of this launch: fbase + 1 .. fbase + depth + 1
+    unsigned* cnt0 = E->sync;                                     // arrivals behind LN0 statistics (+ the final h)
+    unsigned* cnt1 = E->sync + 32;                                // arrivals behind LN1 statistics
+    const unsigned cnt0_base = step * (unsigned)(depth + 1) * (unsigned)G;
+    const unsigned cnt1_base = step * (unsigned)depth * (unsigned)G;
+    unsigned nph = 0;                                             // phase index (profiling slots)
+#define PHASE_DONE()                                                                           \
+    do {                                                                                       \
+        ++nph;                                                                                 \
+        if (c == 0 && tid == 0 && E->prof_on && nph < (unsigned)kProfSlots) {                  \
+            unsigned long long now;                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));                            \
+            E->prof[nph] = now;                                                                \
+        }                                                                                      \
+    } while (0)
+#define PROF3(idx_, which_)                                                                    \
+    do {                                                                                       \
+        if (tid == 0 && E->prof_on) {                                                          \
+            unsigned long long now_;                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                           \
+            E->prof3[((idx_) * 256 + c) * 2 + (which_)] = now_;                                \
+        }                                                                                      \
     } while (0)
     if (c == 0 && tid == 0 && E->prof_on) {
         unsigned long long now;
@@ -971,130 +1064,158 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
 
     // ---- P0: embedding (autoregressive.py:177-197) or an externally embedded activation ------
-    for (int e0 = c * kConsumers; e0 < B * W; e0 += G * kConsumers) {
-        const int e = e0 + tid;
-        const bool act = e < B * W;
-        const int b = act ? e / W : 0, col = act ? e - b * W : 0;
-        float hv = 0.f;
-        if (act) {
-            float x;
+    // This CTA embeds exactly the columns of the residual stream it will own for the whole stack.
+    {
+        const ushort2 wc = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 128)[1];     // column groups of width-W outputs
+        const int ppc = (wc.y * 4) / KS, n_el = B * ppc;
+        float2* res = sm_res();
+        long long* sfx = reinterpret_cast<long long*>(sm_uni() + 32768);
+        for (int e = tid; e < n_el; e += kConsumers) {
+            const int b = e / ppc, pl = e - b * ppc;
+            const int col = wc.x * 8 + 2 * (rank * ppc + pl);
+            float2 x;
             if (A.x_in) {
-                x = A.x_in[e];
+                x = *reinterpret_cast<const float2*>(A.x_in + (size_t)b * W + col);
             } else {
-                if (t == 0) x = A.y_cond ? A.y_cond[e] : E->start_token[col];
-                else x = E->x_emb[(size_t)A.tokens[(size_t)b * A.tok_stride + t - 1] * W + col];
-                x += E->pos_emb[(size_t)t * W + col];
-                if (A.x_cond) x += A.x_cond[((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + col];
+                if (t == 0) x = A.y_cond ? *reinterpret_cast<const float2*>(A.y_cond + (size_t)b * W + col)
+                                         : *reinterpret_cast<const float2*>(E->start_token + col);
+                else x = *reinterpret_cast<const float2*>(E->x_emb + (size_t)A.tokens[(size_t)b * A.tok_stride + t - 1] * W + col);
+                const float2 pe = *reinterpret_cast<const float2*>(E->pos_emb + (size_t)t * W + col);
+                x.x += pe.x; x.y += pe.y;
+                if (A.x_cond) {
+                    const float2 xc = *reinterpret_cast<const float2*>(A.x_cond + ((size_t)b * A.x_cond_len + (A.x_cond_len > 1 ? t : 0)) * W + col);
+                    x.x += xc.x; x.y += xc.y;
+                }
             }
-            const __half hh = __float2half_rn(x);
-            E->h[e] = hh;
-            hv = __half2float(hh);
+            const __half2 hh = __floats2half2_rn(x.x, x.y);
+            const float2 hv = __half22float2(hh);
+            res[b * 32 + pl] = hv;
+            sfx[e] = fx_sum(hv.x) + fx_sum(hv.y);
+            sfx[1024 + e] = fx_sq(hv.x) + fx_sq(hv.y);
+            ll_st(E->ll_h + (((size_t)b * W + col) >> 1), *reinterpret_cast<const uint32_t*>(&hh), fbase + 1);
         }
-        // LayerNorm statistics of layer 0's input: warp-reduce when the warp sits in one row
-        long long s1 = act ? fx_sum(hv) : 0, s2 = act ? fx_sq(hv) : 0;
-        const int b0 = __shfl_sync(0xffffffffu, b, 0);
-        if (__all_sync(0xffffffffu, (!act) || b == b0)) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if ((tid & 31) == 0 && (s1 != 0 || s2 != 0)) {
-                red_add_s64(E->lnacc + 16 * (2 * b0), s1);
-                red_add_s64(E->lnacc + 16 * (2 * b0 + 1), s2);
-            }
-        } else if (act) {
-            red_add_s64(E->lnacc + 16 * (2 * b), s1);
-            red_add_s64(E->lnacc + 16 * (2 * b + 1), s2);
-        }
+        publish_stats(E->lnacc, cnt0, B, ppc, n_el);
     }
-    GRID_BARRIER();
+    PHASE_DONE();
 
 #pragma unroll 1
-    for (int l = 0; l < E->depth; ++l) {
+    for (int l = 0; l < depth; ++l) {
         const LayerDev& LD = *sm_layer(l);
         const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
-        const int pre_ok = attn_prefetch(LD, B, c, t);
+        const uint32_t fl = fbase + (uint32_t)l + 1;              // flag of this layer's buffers
         // a fresh argument record per phase: nothing of it stays live across the calls in between
+        if (l == 1) PROF3(0, 0);
         {
             GemmArgs ga;
-            ga.in = E->h; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y; ga.ln = 1; ga.epi = EPI_QKV;
-            ga.pslot = (int)nbar; ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-            ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.ln_out = nullptr;
+            ga.in = E->ll_h; ga.out = E->ll_qkv; ga.xp = E->xp[0]; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y;
+            ga.ln = 1; ga.epi = EPI_QKV; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
+            ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
+            ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.cnt_in = cnt0; ga.target_in = cnt0_base + (unsigned)(l + 1) * (unsigned)G;
+            ga.ln_out = nullptr; ga.cnt_out = nullptr;
             ring = gemm_phase(ring, B, ga);
+        }
+        if (l == 1) PROF3(0, 1);
+        // LN1 statistics of the previous layer are consumed once every CTA has arrived behind this layer's LN0 (its
+        // proj2 epilogue follows its FC staging).  CTA 0 normally passed that wait inside the phase above; waiting
+        // again costs one L2 hit and covers a CTA 0 without QKV columns (tiny models).
+        if (c == 0 && tid < 32 && l > 0) {
+            if (tid == 0) wait_counter(cnt0, cnt0_base + (unsigned)(l + 1) * (unsigned)G);
+            __syncwarp();
+            E->lnacc[(size_t)(2 * l - 1) * 512 + 16 * tid] = 0;
         }
         // next layer's record + column assignment -> the other shared-memory slot.  The descriptor is in
         // HBM (the weight stream evicts it from L2 every step): issue the loads here so their latency hides
-        // behind the barrier instead of sitting on the dependency chain.
-        if (l + 1 < E->depth) {
+        // behind the attention phase instead of sitting on the dependency chain.
+        if (l + 1 < depth) {
             if (tid < (int)(sizeof(LayerDev) / 4))
                 reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1))[tid] =
                     reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1])[tid];
             if (tid >= 32 && tid < 36)
                 reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1) + 128)[tid - 32] =
-                    reinterpret_cast<const uint32_t*>(E->cols + ((size_t)c * E->depth + l + 1) * 4)[tid - 32];
+                    reinterpret_cast<const uint32_t*>(E->cols + ((size_t)unit * depth + l + 1) * 4)[tid - 32];
         }
-        GRID_BARRIER();
+        PHASE_DONE();
+        if (l == 1) PROF3(1, 0);
         {
             const AttnGeom geo = attn_geom(E, LD, t);
-            const int ns = attn_nsplit(E, B, geo.R - (geo.cur ? 1 : 0));
+            const int ns = attn_nsplit(E, B, geo.R - ((geo.R > 0 && geo.cur) ? 1 : 0));
             for (int it = c; it < B * E->H * ns; it += G) {
                 const int s = it % ns, bh = it / ns;
-                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nbar, pre_ok && it == c);
-            }
-            STAMP(E, (int)nbar, 4);
-            ++nbar;
-            ndone += (unsigned)(B * E->H);
-            attn_done_wait(E, done0 + ndone);
-            STAMP(E, (int)nbar - 1, 5);
-            if (c == 0 && tid == 0 && E->prof_on && nbar < (unsigned)kProfSlots) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                E->prof[nbar] = now;
+                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nph, fl);
+                consumer_sync();           // tile / q regions are reused by the next item or the next phase
             }
         }
-        if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;      // LN0 statistics of this layer are consumed
+        if (l == 1) PROF3(1, 1);
+        PHASE_DONE();
+        if (l == 1) PROF3(2, 0);
         {
             GemmArgs ga;
-            ga.in = E->a; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y; ga.ln = 0; ga.epi = EPI_PROJ;
-            ga.pslot = (int)nbar; ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
-            ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512;
+            ga.in = E->ll_a; ga.out = E->ll_x1; ga.xp = E->xp[1]; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y;
+            ga.ln = 0; ga.epi = EPI_PROJ; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
+            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.cnt_in = nullptr; ga.target_in = 0;
+            ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512; ga.cnt_out = cnt1;
             ring = gemm_phase(ring, B, ga);
         }
-        GRID_BARRIER();
+        if (l == 1) PROF3(2, 1);
+        PHASE_DONE();
+        if (l == 1) PROF3(3, 0);
         {
             GemmArgs ga;
-            ga.in = E->x1; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y; ga.ln = 1; ga.epi = EPI_FC;
-            ga.pslot = (int)nbar; ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-            ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.ln_out = nullptr;
+            ga.in = E->ll_x1; ga.out = E->ll_g; ga.xp = E->xp[2]; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y;
+            ga.ln = 1; ga.epi = EPI_FC; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
+            ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
+            ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.cnt_in = cnt1; ga.target_in = cnt1_base + (unsigned)(l + 1) * (unsigned)G;
+            ga.ln_out = nullptr; ga.cnt_out = nullptr;
             ring = gemm_phase(ring, B, ga);
         }
-        GRID_BARRIER();
-        if (c == 0 && tid < 32) E->lnacc[(size_t)(2 * l + 1) * 512 + 16 * tid] = 0;  // LN1 statistics are consumed
+        if (l == 1) PROF3(3, 1);
+        // LN0 statistics of this layer are consumed once every CTA has arrived behind LN1 (proj epilogue follows QKV staging)
+        if (c == 0 && tid < 32) {
+            if (tid == 0) wait_counter(cnt1, cnt1_base + (unsigned)(l + 1) * (unsigned)G);
+            __syncwarp();
+            E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;
+        }
+        PHASE_DONE();
+        if (l == 1) PROF3(4, 0);
         {
             GemmArgs ga;
-            ga.in = E->g; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y; ga.ln = 0; ga.epi = EPI_PROJ2;
-            ga.pslot = (int)nbar; ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
-            ga.ln_out = (l + 1 < E->depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr;
+            ga.in = E->ll_g; ga.out = E->ll_h; ga.xp = E->xp[3]; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y;
+            ga.ln = 0; ga.epi = EPI_PROJ2; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl + 1;
+            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr; ga.cnt_in = nullptr; ga.target_in = 0;
+            ga.ln_out = (l + 1 < depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr; ga.cnt_out = cnt0;
             ring = gemm_phase(ring, B, ga);
         }
-        GRID_BARRIER();
+        if (l == 1) PROF3(4, 1);
+        PHASE_DONE();
     }
-    if (A.h_out) {
-        for (int e = c * kConsumers + tid; e < B * W; e += G * kConsumers)
-            A.h_out[e] = ld_half_cg(E->h + e);
+    if (A.h_out) {      // Transformer.forward boundary: this CTA's slice of the residual stream
+        const ushort2 wc = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * ((depth - 1) & 1) + 128)[1];
+        const int ppc = (wc.y * 4) / KS;
+        const float2* res = sm_res();
+        for (int e = tid; e < B * ppc; e += kConsumers) {
+            const int b = e / ppc, pl = e - b * ppc;
+            const int col = wc.x * 8 + 2 * (rank * ppc + pl);
+            *reinterpret_cast<float2*>(A.h_out + (size_t)b * W + col) = res[b * 32 + pl];
+        }
     }
-    if (do_logits) logits_phase(A, ring, c, t);
-    if (c == 0 && tid == 0) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (E->prof_on && nbar + 1 < (unsigned)kProfSlots) E->prof[nbar + 1] = now;
-        *E->t = t + 1;
-        *E->epoch = epoch0 + nreal;
-        *(E->bar + 1600) = done0 + ndone;
+    if (do_logits) logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
+    if (c == 0) {
+        // the last arrival: every CTA is through its last LN1 staging, its statistics can be cleared; then the
+        // bookkeeping of the launch
+        if (tid == 0) wait_counter(cnt0, cnt0_base + (unsigned)(depth + 1) * (unsigned)G);
+        consumer_sync();
+        if (tid < 32) E->lnacc[(size_t)(2 * depth - 1) * 512 + 16 * tid] = 0;
+        if (tid == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (E->prof_on && nph + 1 < (unsigned)kProfSlots) E->prof[nph + 1] = now;
+            *E->t = t + 1;
+            *(E->sync + 64) = step + 1;
+        }
     }
-#undef GRID_BARRIER
+#undef PHASE_DONE
+#undef PROF3
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1108,21 +1229,22 @@ template <>
 __device__ __forceinline__ __half to_half<__half>(__half v) { return v; }
 
 // src: Conv1D.w [K][N] row-major.  dst: per-CTA streams; this kernel fills GEMM `gi` of layer `l`.
-// grid.x = CTA index c, threads loop over this CTA's (kk, j, lane) fragment slots.
+// grid.x = CTA index c = unit * KS + rank: the unit's column groups, the rank's K slice; threads loop over this
+// CTA's (kk, j, lane) fragment slots.
 template <typename T>
 __global__ void pack_gemm_kernel(const T* __restrict__ src, int K, int N, uint8_t* streams,
                                  unsigned long long stream_stride, const ushort2* cols, const uint32_t* goff,
-                                 int depth, int l, int gi) {
+                                 int depth, int l, int gi, int KS) {
     const int c = blockIdx.x;
-    const ushort2 cg = cols[((size_t)c * depth + l) * 4 + gi];
+    const ushort2 cg = cols[((size_t)(c / KS) * depth + l) * 4 + gi];
     const int g0 = cg.x, ncg = cg.y;
     if (ncg == 0) return;
     uint8_t* dst = streams + (size_t)c * stream_stride + (size_t)goff[((size_t)c * depth + l) * 4 + gi] * 16;
-    const int nkk = K >> 4;
+    const int nkk = (K / KS) >> 4, kk_first = (c % KS) * nkk;
     const int total = nkk * ncg * 32;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int lane = i & 31, u = i >> 5;
-        const int j = u % ncg, kk = u / ncg;
+        const int j = u % ncg, kk = kk_first + u / ncg;
         const int n = (g0 + j) * 8 + (lane >> 2);
         const int k = kk * 16 + (lane & 3) * 2;
         __half v[4];
@@ -1184,18 +1306,19 @@ __global__ void enc_kv_scatter_kernel(const __half* __restrict__ y, __half* kc, 
 namespace {
 
 struct Layout {
-    size_t off_dev, off_cols, off_soff, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_encx, off_ency, off_wt, off_pf, off_sync, total;
+    size_t off_dev, off_cols, off_goff, off_lrow, off_streams, off_small, off_cache, off_h, off_x1, off_qkv, off_a, off_g, off_xp[4], off_part, off_acnt, off_prof, off_prof2, off_prof3, off_lnacc, off_encx, off_ency, off_wt, off_pf, off_sync, total;
+    int KS, U;
     size_t wt_per_layer;
     int pf_len, pf_rows;
     size_t stream_stride;
     std::vector<ushort2> cols;
-    std::vector<uint32_t> soff, goff;
+    std::vector<uint32_t> goff;
     std::vector<int> lrow;
     std::vector<size_t> cache_off;      // per layer (K); V follows
     std::vector<size_t> cache_bytes;
     std::vector<int> cache_rows;
     size_t small_per_layer;
-    int dh, dh_pad, bc, prime_pad, uni_bytes, kvpre_bytes, kv_prefetch, nslot, smem_bytes;
+    int dh, dh_pad, bc, prime_pad, uni_bytes, kvpre_bytes, kv_prefetch, nslot, smem_bytes, RC;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1224,12 +1347,30 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     L.bc = c.blocks > 0 ? c.n_ctx / c.blocks : c.n_ctx;
     JK_REQUIRE(c.blocks == 0 || c.n_ctx % c.blocks == 0, "n_ctx %% blocks != 0");
     L.prime_pad = c.blocks > 0 ? (c.prime_len / c.blocks + 1) * c.blocks : 0;
+    JK_REQUIRE(L.dh % 2 == 0, "head_dim %d must be even", L.dh);
     const int depth = c.depth;
-    L.cols.assign((size_t)G * depth * 4, make_ushort2(0, 0));
+    // K-split factor: CTAs form units of KS that share column groups and split K.  The largest of 4 / 2 / 1 for which
+    // every Conv1D's K splits into whole 16-row MMA steps and no unit gets more than 8 column groups.
+    {
+        int want = 4;
+        if (const char* e = getenv("JK_KSPLIT")) want = atoi(e);
+        const int Ks_all[3] = {c.width, c.n_state, c.mlp_width};
+        const int Nmax = std::max(std::max(3 * c.n_state, c.width), c.mlp_width);
+        int ks = 1;
+        for (int cand = 4; cand >= 1; cand >>= 1) {
+            if (cand > want || G % cand) continue;
+            bool ok = true;
+            for (int i = 0; i < 3; ++i) ok = ok && ((Ks_all[i] / 16) % cand == 0);
+            ok = ok && ((Nmax / 8 + G / cand - 1) / (G / cand) <= 8);
+            if (ok) { ks = cand; break; }
+        }
+        L.KS = ks; L.U = G / ks;
+    }
+    const int KS = L.KS, U = L.U;
+    L.cols.assign((size_t)U * depth * 4, make_ushort2(0, 0));
     L.goff.assign((size_t)G * depth * 4, 0);
-    L.soff.assign((size_t)G * (depth + 1), 0);
-    std::vector<unsigned long long> cum(G, 0);
-    std::vector<int> order(G);
+    std::vector<unsigned long long> cum(U, 0);        // bytes per CTA of a unit (all ranks of a unit stream the same amount)
+    std::vector<int> order(U);
     for (int l = 0; l < depth; ++l) {
         const int af = c.attn_func[l];
         JK_REQUIRE(af == 0 || af == 1 || af == 2 || af == 3 || af == 6 || af == 7, "attn_func %d has no decode path", af);
@@ -1238,56 +1379,63 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
         const int Ns[4] = {af == 6 ? c.n_state : 3 * c.n_state, c.width, c.mlp_width, c.width};
         for (int gi = 0; gi < 4; ++gi) {
             JK_REQUIRE(Ns[gi] % 8 == 0, "n_out %d not a multiple of 8", Ns[gi]);
-            const int groups = Ns[gi] / 8, base = groups / G, extra = groups % G;
-            JK_REQUIRE(base + (extra ? 1 : 0) <= 8, "n_out %d too wide for %d CTAs (max 64 columns per CTA)", Ns[gi], G);
-            for (int i = 0; i < G; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cum[a] < cum[b]; });
-            std::vector<int> n(G, base);
-            for (int i = 0; i < extra; ++i) n[order[i]] += 1;
+            const int groups = Ns[gi] / 8, base = groups / U, extra = groups % U;
+            JK_REQUIRE(base + (extra ? 1 : 0) <= 8, "n_out %d too wide for %d units (max 64 columns per unit)", Ns[gi], U);
+            std::vector<int> n(U, base);
+            if (gi == 1 || gi == 3) {
+                // width-W outputs (proj, proj2, and the embedding): ONE fixed assignment for the whole stack, because the
+                // CTA that finishes a column keeps that column of the residual stream in its shared memory
+                for (int i = 0; i < extra; ++i) n[i] += 1;
+            } else {
+                for (int i = 0; i < U; ++i) order[i] = i;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cum[a] < cum[b]; });
+                for (int i = 0; i < extra; ++i) n[order[i]] += 1;
+            }
             int g0 = 0;
-            for (int cta = 0; cta < G; ++cta) {
-                L.cols[((size_t)cta * depth + l) * 4 + gi] = make_ushort2((unsigned short)g0, (unsigned short)n[cta]);
-                L.goff[((size_t)cta * depth + l) * 4 + gi] = (uint32_t)(cum[cta] / 16);
-                if (gi == 0) L.soff[(size_t)cta * (depth + 1) + l] = (uint32_t)(cum[cta] / 16);
-                cum[cta] += (unsigned long long)n[cta] * (Ks[gi] / 16) * 256ull;
-                g0 += n[cta];
+            for (int u = 0; u < U; ++u) {
+                L.cols[((size_t)u * depth + l) * 4 + gi] = make_ushort2((unsigned short)g0, (unsigned short)n[u]);
+                for (int r = 0; r < KS; ++r)
+                    L.goff[((size_t)(u * KS + r) * depth + l) * 4 + gi] = (uint32_t)(cum[u] / 16);
+                cum[u] += (unsigned long long)n[u] * (Ks[gi] / KS / 16) * 256ull;
+                g0 += n[u];
             }
         }
     }
     unsigned long long mx = 0;
-    for (int cta = 0; cta < G; ++cta) {
-        L.soff[(size_t)cta * (depth + 1) + depth] = (uint32_t)(cum[cta] / 16);
-        mx = std::max(mx, cum[cta]);
-    }
+    for (int u = 0; u < U; ++u) mx = std::max(mx, cum[u]);
     JK_REQUIRE(mx / 16 < 0xffffffffull, "stream too long");
     L.stream_stride = align_up((size_t)mx + 256, 256);
     L.lrow.assign(G + 1, 0);
     for (int cta = 0; cta <= G; ++cta) L.lrow[cta] = (int)((long long)c.bins * cta / G);
 
-    const int Kmax = std::max(c.width, std::max(c.n_state, c.mlp_width));
-    size_t uni = (size_t)16 * (Kmax + 8) * 2;
-    uni = std::max(uni, (size_t)16 * kLogitKT * 4);
-    uni = std::max(uni, (size_t)8 * 8 * 16 * 8 * 4);                              // cross-warp reduction
-    const int RC = attn_tile_rows(L.dh_pad);
-    const size_t kv_stage = (size_t)2 * RC * L.dh_pad * 2;                        // one K tile + one V tile
-    size_t attn = kv_stage + (size_t)L.dh_pad * 2 + 64 * 4 + (size_t)L.dh_pad * 4 + 64;   // tiles, q, scores, running output
-    uni = std::max(uni, attn);
-    L.uni_bytes = (int)align_up(uni, 1024);
+    const int Kmax = std::max(c.width, std::max(c.n_state, c.mlp_width)) / KS;
+    const int act_rows = c.max_batch > 8 ? 16 : 8;      // rows >= n_samples of the A tile are never read back (see stage_acts)
     const int max_smem = 232448;
-    L.kvpre_bytes = (int)align_up(kv_stage, 1024);      // second K/V stage: prefetch target / double buffer
-    // prefetching the first attention tile before the QKV GEMM hides its latency but costs more issue time
-    // than it saves (measured 2703 vs 2653 us / step at position 4000): off unless JK_KV_PREFETCH is set
-    L.kv_prefetch = getenv("JK_KV_PREFETCH") ? 1 : 0;
-    int nslot = (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes;
+    int RC = attn_tile_rows(L.dh_pad), nslot = 0;
+    for (;; RC >>= 1) {
+        size_t uni = (size_t)act_rows * (Kmax + 8) * 2;
+        uni = std::max(uni, (size_t)16 * kLogitKT * 4);
+        uni = std::max(uni, (size_t)32768 + 2 * 1024 * 8);                           // cross-warp reduction + statistics scratch
+        const size_t kv_stage = (size_t)2 * RC * L.dh_pad * 2;                        // one K tile + one V tile
+        size_t attn = kv_stage + (size_t)3 * L.dh_pad * 2 + 64 * 4 + (size_t)L.dh_pad * 4 + 64;   // tiles, q/k/v, scores, running output
+        uni = std::max(uni, attn);
+        L.uni_bytes = (int)align_up(uni, 1024);
+        L.kvpre_bytes = (int)align_up(kv_stage, 1024);      // second K/V stage (double buffer of multi-tile parts)
+        nslot = (max_smem - kHeaderBytes - L.uni_bytes - L.kvpre_bytes) / kSlotBytes;
+        if (nslot >= 4 || RC <= 16) break;                  // a deep weight ring matters more than tall K/V tiles
+    }
+    L.RC = RC;
+    L.kv_prefetch = 0;
     nslot = std::min(nslot, kMaxSlots);
     JK_REQUIRE(nslot >= 2, "not enough shared memory for the weight ring (uni %d bytes)", L.uni_bytes);
     L.nslot = nslot;
     L.smem_bytes = kHeaderBytes + L.uni_bytes + L.kvpre_bytes + nslot * kSlotBytes;
+    // ldmatrix always addresses 16 A-tile rows; with an 8-row tile rows 8..15 must still lie inside the allocation
+    JK_REQUIRE((size_t)kHeaderBytes + (size_t)16 * (Kmax + 8) * 2 <= (size_t)L.smem_bytes, "A tile exceeds shared memory");
 
     size_t off = 0;
     L.off_dev = off; off = align_up(off + sizeof(EngineDev), 256);
     L.off_cols = off; off = align_up(off + L.cols.size() * sizeof(ushort2), 256);
-    L.off_soff = off; off = align_up(off + L.soff.size() * 4, 256);
     L.off_goff = off; off = align_up(off + L.goff.size() * 4, 256);
     L.off_lrow = off; off = align_up(off + L.lrow.size() * 4, 256);
     L.off_streams = off; off = align_up(off + (size_t)G * L.stream_stride, 256);
@@ -1305,17 +1453,19 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
         L.cache_off[l] = off; L.cache_bytes[l] = bytes;
         off += 2 * bytes;
     }
-    L.off_h = off;   off = align_up(off + (size_t)16 * c.width * 2, 256);
-    L.off_x1 = off;  off = align_up(off + (size_t)16 * c.width * 2, 256);
-    L.off_qkv = off; off = align_up(off + (size_t)16 * 3 * c.n_state * 2, 256);
-    L.off_a = off;   off = align_up(off + (size_t)16 * c.n_state * 2, 256);
-    L.off_g = off;   off = align_up(off + (size_t)16 * c.mlp_width * 2, 256);
+    // LL activation buffers: 8 bytes per fp16 PAIR ({half2, flag})
+    L.off_h = off;   off = align_up(off + (size_t)16 * c.width * 4, 256);
+    L.off_x1 = off;  off = align_up(off + (size_t)16 * c.width * 4, 256);
+    L.off_qkv = off; off = align_up(off + (size_t)16 * 3 * c.n_state * 4, 256);
+    L.off_a = off;   off = align_up(off + (size_t)16 * c.n_state * 4, 256);
+    L.off_g = off;   off = align_up(off + (size_t)16 * c.mlp_width * 4, 256);
+    for (int gi = 0; gi < 4; ++gi) { L.off_xp[gi] = off; off = align_up(off + (size_t)G * 16 * kXpCols * 8, 256); }
     L.off_part = off; off = align_up(off + (size_t)c.max_batch * c.heads * kMaxSplit * (L.dh_pad + 2) * 4, 256);
     L.off_acnt = off; off = align_up(off + (size_t)c.max_batch * c.heads * 4, 256);
     L.off_prof = off; off = align_up(off + (size_t)kProfSlots * 8, 256);
     L.off_prof2 = off; off = align_up(off + (size_t)kProfSlots * 8 * 8, 256);
     L.off_prof3 = off; off = align_up(off + (size_t)5 * 256 * 2 * 8, 256);
-    L.off_lnacc = off; off = align_up(off + (size_t)2 * depth * 512 * 8, 256);
+    L.off_lnacc = off; off = align_up(off + (size_t)(2 * depth + 1) * 512 * 8, 256);
     {
         bool any6 = false;
         for (int l = 0; l < depth; ++l) any6 = any6 || (c.attn_func[l] == 6);
@@ -1381,35 +1531,35 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     p->cfg = *cfg; p->arena = (uint8_t*)arena; p->arena_bytes = arena_bytes; p->G = G; p->t_host = 0;
     p->smem_bytes = L.smem_bytes;
     p->cols = L.cols; p->goff = L.goff;
+    if (getenv("JK_VERBOSE"))
+        fprintf(stderr, "jk_prior_create: G %d, KS %d, units %d, tile rows %d, ring %d x %d B, uni %d B, smem %d B, arena %.1f MB\n", G, L.KS,
+                L.U, L.RC, L.nslot, kSlotBytes, L.uni_bytes, L.smem_bytes, L.total / 1e6);
     uint8_t* A = p->arena;
     EngineDev& E = p->host;
     memset(&E, 0, sizeof(E));
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.kv_prefetch = L.kv_prefetch; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
+    E.depth = cfg->depth; E.G = G; E.KS = L.KS; E.U = L.U; E.RC = L.RC; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);
     }
     E.cols = (const ushort2*)(A + L.off_cols);
-    E.soff = (const uint32_t*)(A + L.off_soff);
     p->d_cols = (ushort2*)(A + L.off_cols);
     p->d_goff = (uint32_t*)(A + L.off_goff);
     E.lrow0 = (const int*)(A + L.off_lrow);
     E.streams = A + L.off_streams; E.stream_stride = L.stream_stride;
-    E.h = (__half*)(A + L.off_h); E.x1 = (__half*)(A + L.off_x1); E.qkv = (__half*)(A + L.off_qkv);
-    E.a = (__half*)(A + L.off_a); E.g = (__half*)(A + L.off_g); E.part = (float*)(A + L.off_part);
+    E.ll_h = (unsigned long long*)(A + L.off_h); E.ll_x1 = (unsigned long long*)(A + L.off_x1);
+    E.ll_qkv = (unsigned long long*)(A + L.off_qkv); E.ll_a = (unsigned long long*)(A + L.off_a);
+    E.ll_g = (unsigned long long*)(A + L.off_g);
+    for (int gi = 0; gi < 4; ++gi) E.xp[gi] = (unsigned long long*)(A + L.off_xp[gi]);
+    E.part = (float*)(A + L.off_part);
     E.acnt = (unsigned*)(A + L.off_acnt); E.prof = (unsigned long long*)(A + L.off_prof);
     E.lnacc = (long long*)(A + L.off_lnacc);
     E.prof2 = (long long*)(A + L.off_prof2);
     E.prof3 = (unsigned long long*)(A + L.off_prof3);
-    {
-        const char* sr = getenv("JK_ATTN_SPLIT_ROWS");
-        E.split_rows = sr ? atoi(sr) : 96;
-        if (E.split_rows < 8) E.split_rows = 8;
-    }
-    E.bar = (unsigned*)(A + L.off_sync); E.epoch = E.bar + 1536; E.t = (int*)(E.bar + 1568);
+    E.sync = (unsigned*)(A + L.off_sync); E.t = (int*)(E.sync + 96);
     size_t enc_off = L.off_small + L.small_per_layer * cfg->depth;
     for (int i = 0; i < 4; ++i) { p->bias_ptr[i].resize(cfg->depth); p->ln_ptr[i].resize(cfg->depth); }
     p->enc_w.assign(cfg->depth, nullptr); p->enc_b.assign(cfg->depth, nullptr);
@@ -1456,12 +1606,18 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     }
     p->dev = (EngineDev*)(A + L.off_dev);
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_cols, L.cols.data(), L.cols.size() * sizeof(ushort2), cudaMemcpyHostToDevice, stream));
-    JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_soff, L.soff.data(), L.soff.size() * 4, cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_goff, L.goff.data(), L.goff.size() * 4, cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaMemcpyAsync(A + L.off_lrow, L.lrow.data(), L.lrow.size() * 4, cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaMemcpyAsync(p->dev, &p->host, sizeof(EngineDev), cudaMemcpyHostToDevice, stream));
     JK_CHECK_CUDA(cudaStreamSynchronize(stream));      // the host vectors above go out of scope
-    JK_CHECK_CUDA(cudaFuncSetAttribute(jk_decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    {   // the attribute belongs to the KERNEL, not to this engine: engines of different configurations coexist
+        // (5b_lyrics: lyric encoder + decoder), so it is raised to the device's opt-in maximum once and never lowered
+        int dev = 0, optin = 0;
+        JK_CHECK_CUDA(cudaGetDevice(&dev));
+        JK_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        JK_REQUIRE(L.smem_bytes <= optin, "decode kernel needs %d bytes of shared memory, device allows %d", L.smem_bytes, optin);
+        JK_CHECK_CUDA(cudaFuncSetAttribute(jk_decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    }
     *out = p;
     return 0;
 }
@@ -1474,7 +1630,7 @@ extern "C" int jk_prior_destroy(jk_prior* p) {
 template <typename T>
 static int pack_one(jk_prior* p, const void* w, int K, int N, int l, int gi, cudaStream_t stream) {
     pack_gemm_kernel<T><<<p->G, 256, 0, stream>>>((const T*)w, K, N, (uint8_t*)p->host.streams, p->host.stream_stride,
-                                                   p->d_cols, p->d_goff, p->cfg.depth, l, gi);
+                                                   p->d_cols, p->d_goff, p->cfg.depth, l, gi, p->host.KS);
     JK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1578,6 +1734,7 @@ extern "C" int jk_prior_step(jk_prior* p, const jk_step_args* a, jk_stream_t str
     JK_REQUIRE(p && a, "null argument");
     JK_REQUIRE(a->n_samples >= 1 && a->n_samples <= p->cfg.max_batch, "n_samples %d out of range (max_batch %d)",
                a->n_samples, p->cfg.max_batch);
+    JK_REQUIRE(p->t_host < p->cfg.n_ctx, "position %d is past the context (n_ctx %d): reset the engine", p->t_host, p->cfg.n_ctx);
     JK_REQUIRE(a->x_in || a->tokens || p->t_host == 0, "tokens required for t > 0");
     JK_REQUIRE(a->x_in || (p->host.pos_emb && p->host.x_emb), "embeddings not set (jk_prior_set_embeddings)");
     JK_REQUIRE(!a->logits || p->host.x_out, "x_out not set");
@@ -1604,11 +1761,7 @@ extern "C" int jk_prior_debug_buffer(const jk_prior* p, int which, const void** 
     JK_REQUIRE(p && ptr && n, "null argument");
     const jk_prior_config& c = p->cfg;
     switch (which) {
-        case 0: *ptr = p->host.h; *n = (size_t)16 * c.width; break;
-        case 1: *ptr = p->host.qkv; *n = (size_t)16 * 3 * c.n_state; break;
-        case 2: *ptr = p->host.a; *n = (size_t)16 * c.n_state; break;
-        case 3: *ptr = p->host.x1; *n = (size_t)16 * c.width; break;
-        case 4: *ptr = p->host.g; *n = (size_t)16 * c.mlp_width; break;
+        /* 0..4 were the fp16 intermediates of round 1; activations now travel as LL words between SMs */
         case 5: *ptr = p->host.prof; *n = (size_t)kProfSlots * 4; break;     /* uint64 timestamps */
         case 7: *ptr = p->host.prof3; *n = (size_t)5 * 256 * 2 * 4; break;
         case 6: *ptr = p->host.prof2; *n = (size_t)kProfSlots * 8 * 4; break; /* int64 clock64 stamps [slot][8] */

@@ -19,22 +19,24 @@ struct LayerDev {
 
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
-    int nslot, uni_bytes, kvpre_bytes, kv_prefetch, small_bytes, prof_on;
+    int RC;                         // rows of one shared-memory K (or V) tile of the attention phase
+    int KS, U;                      // K-split factor of every Conv1D and the number of column units (G = U * KS)
+    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on;
     float scale2;
-    const ushort2* cols;            // [G][depth][4] : (first 8-column group, number of groups)
-    const uint32_t* soff;           // [G][depth+1]  : stream offset of each layer, in 16-B units
+    const ushort2* cols;            // [U][depth][4] : (first 8-column group, number of groups) of a unit
     const uint8_t* streams;
     unsigned long long stream_stride;
-    __half *h, *qkv, *a, *x1, *g;   // [16][.] fp16 activations
+    // activations between phases travel as "LL" words (NCCL's low-latency protocol): 8 bytes = {half2 data, u32 flag},
+    // written with one 8-byte store and polled by the consumer - no separate flag, no grid barrier
+    unsigned long long *ll_h, *ll_x1, *ll_qkv, *ll_a, *ll_g;   // [16][N/2]
+    unsigned long long* xp[4];      // K-split partial sums {fp32, flag}: [G][16][64] per Conv1D of a layer
     float* part;                    // split-KV partials [Bmax*H*kMaxSplit][dh_pad + 2]
     unsigned* acnt;                 // [Bmax*H] merge tickets
-    long long* lnacc;               // [2*depth][16][2] fixed-point LayerNorm accumulators (sum, sumsq)
-    int split_rows;                 // attention: rows per part before a (sample, head) is split over CTAs
+    long long* lnacc;               // [2*depth][16][2] fixed-point LayerNorm accumulators (sum, sumsq), 128-B apart
     long long* prof2;               // [kProfSlots][8] intra-phase clock64 stamps of CTA 0 (tuning aid)
-    unsigned long long* prof3;      // [5][256][2] per-CTA barrier arrival / exit times of layer 1
+    unsigned long long* prof3;      // [5][256][2] per-CTA phase entry / exit times of layer 1
     unsigned long long* prof;       // [kProfSlots] phase timestamps of CTA 0 (globaltimer ns)
-    unsigned* bar;
-    unsigned* epoch;
+    unsigned* sync;                 // [0] LN0 arrivals, [32] LN1 arrivals, [64] steps executed (one 128-B line each)
     int* t;
     const float *x_emb, *pos_emb, *x_out, *start_token;
     const int* lrow0;               // [G+1] logits rows per CTA (prefix)
@@ -57,7 +59,7 @@ struct jk_prior {
     int G;
     int smem_bytes;
     int t_host;
-    std::vector<ushort2> cols;
+    std::vector<ushort2> cols;       // [U][depth][4]
     std::vector<uint32_t> goff;      // [G][depth][4] per-GEMM stream offsets (16-B units)
     uint32_t* d_goff;
     ushort2* d_cols;

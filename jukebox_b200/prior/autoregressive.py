@@ -75,7 +75,6 @@ class ConditionalAutoregressive2D(nn.Module):
             self.x_out = nn.Linear(width, bins, bias=False)
             if self.share_x_emb_x_out:
                 self.x_out.weight = self.x_emb.weight
-        self._emb_key = None
 
     # ---- token <-> tensor layout (reference :100-112) -------------------------------------------
     def preprocess(self, x):
@@ -96,12 +95,14 @@ class ConditionalAutoregressive2D(nn.Module):
         eng = tr.engine(n_samples)
         x_out = None if self.only_encode else self.x_out.weight
         start = None if self.y_cond else self.start_token
-        key = (id(eng), self.x_emb.weight.data_ptr(), self.pos_emb.pos_emb.data_ptr(),
+        # the key lives ON the engine object: a freshly built engine (drop_engine after .cuda() /
+        # load_state_dict) always starts without embeddings, whatever address CPython gives it
+        key = (self.x_emb.weight.data_ptr(), self.pos_emb.pos_emb.data_ptr(),
                None if x_out is None else x_out.data_ptr(), None if start is None else start.data_ptr())
-        if key != self._emb_key:
+        if getattr(eng, "_emb_key", None) != key:
             eng.set_embeddings(x_emb=self.x_emb.weight, pos_emb=self.pos_emb.pos_emb, x_out=x_out,
                                start_token=None if start is None else start.view(-1))
-            self._emb_key = key
+            eng._emb_key = key
         return eng
 
     def _check_conds(self, N, x_cond, y_cond):
@@ -123,59 +124,10 @@ class ConditionalAutoregressive2D(nn.Module):
 
     def _run(self, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p, get_preds, sample_tokens):
         """shared body of sample / primed_sample.  prime: LongTensor [N, P] of given tokens (P may be 0)."""
-        assert self.training is False
-        assert not self.only_encode
-        if not fp16:
-            raise NotImplementedError("fp32 sampling is not built; use fp16=True (the reference's sampling_kwargs)")
-        if sample_tokens is None:
-            sample_tokens = self.input_dims
-        N = n_samples
-        x_cond, y_cond = self._check_conds(N, x_cond, y_cond)
-        P = prime.shape[1]
-        assert P < sample_tokens
-        dev = self.x_emb.weight.device
-        eng = self._engine(N)
-        tr = self.transformer
-        tr.del_cache()
-        if any(b.attn_func == 6 for b in tr._attn_mods):
-            assert encoder_kv is not None
-            eng.set_encoder_kv(encoder_kv)
-        tokens = t.zeros(N, sample_tokens, dtype=t.long, device=dev)
-        if P:
-            assert (0 <= prime).all() and (prime < self.bins).all()
-            tokens[:, :P] = prime
-        if get_preds:
-            preds = t.empty(N, sample_tokens, self.bins, dtype=t.float32, device=dev)
-            lbuf, tstride = preds, self.bins
-        else:
-            lbuf, tstride = t.empty(N, self.bins, dtype=t.float32, device=dev), 0
-        # the key of this call's Philox stream comes from torch's default generator, so t.manual_seed /
-        # seed_per_rank make sampling reproducible exactly as they do for the reference's Categorical
-        seed = int(t.empty((), dtype=t.int64).random_().item())
-        with t.no_grad():
-            start = 0
-            if P > 1 and not get_preds and 1 < P <= eng.prefill_capacity:
-                # the given tokens go through all layers at once (the reference's chunked primed_sample,
-                # autoregressive.py:300-338); chunk_size is moot - one chunk
-                eng.prefill(N, P, tokens=tokens, y_cond=y_cond, x_cond=x_cond)
-                start = P
-            for sample_t in get_range(range(start, sample_tokens)):
-                need = get_preds or sample_t >= P
-                eng.step(N, tokens=tokens, y_cond=y_cond, x_cond=x_cond, logits=lbuf if need else None,
-                         logits_tstride=tstride)
-                if sample_t >= P:
-                    x = preds[:, sample_t] if get_preds else lbuf
-                    if top_k or top_p:      # filtering keeps the reference's torch expression (ops.py:99-122)
-                        x = filter_logits(x / temp, top_k=top_k, top_p=top_p).contiguous()
-                        sample_categorical(x, 1.0, seed, sample_t, tokens)
-                    else:
-                        sample_categorical(x, temp, seed, sample_t, tokens)
-            for b in tr._attn_mods:
-                b.attn._advance(N, sample_tokens, fp16)
-            tr.check_cache(N, sample_tokens, fp16)
-            tr.del_cache()
-            x = self.postprocess(tokens, sample_tokens)
-        return (x, preds) if get_preds else x
+        win = SamplingWindow(self, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p,
+                             get_preds, sample_tokens)
+        win.advance(win.sample_tokens)
+        return win.finish()
 
     # ---- reference API -----------------------------------------------------------------------
     def sample(self, n_samples, x_cond=None, y_cond=None, encoder_kv=None, fp16=False, temp=1.0, top_k=0,
@@ -224,3 +176,85 @@ class ConditionalAutoregressive2D(nn.Module):
             if self.add_cond_after_transformer and x_cond is not None:
                 acts = acts + x_cond
         return acts
+
+
+class SamplingWindow:
+    """One sampling window in flight on the decode engine: the body of the reference's sample loop
+    (prior/autoregressive.py:222-237, 300-345) split into begin / advance / finish, so that callers which
+    need the window in pieces (bench.py times 1/8-window slices) drive the same code as `sample`.
+
+    begin (constructor): caches emptied, encoder K/V loaded, the given tokens prefilled in one pass when the
+    engine can (else they are stepped by `advance`).  advance(upto): one decode launch + one sampling launch
+    per position, nothing synchronises with the host.  finish(): cache bookkeeping + postprocess."""
+
+    def __init__(self, ca, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p, get_preds,
+                 sample_tokens):
+        assert ca.training is False
+        assert not ca.only_encode
+        if not fp16:
+            raise NotImplementedError("fp32 sampling is not built; use fp16=True (the reference's sampling_kwargs)")
+        self.ca = ca
+        self.sample_tokens = ca.input_dims if sample_tokens is None else int(sample_tokens)
+        self.N = N = n_samples
+        self.x_cond, self.y_cond = ca._check_conds(N, x_cond, y_cond)
+        self.P = P = prime.shape[1]
+        assert P < self.sample_tokens <= ca.input_dims, \
+            f"need given tokens {P} < sample_tokens {self.sample_tokens} <= input_dims {ca.input_dims}"
+        dev = ca.x_emb.weight.device
+        self.eng = eng = ca._engine(N)
+        self.tr = tr = ca.transformer
+        tr.del_cache()
+        if any(b.attn_func == 6 for b in tr._attn_mods):
+            assert encoder_kv is not None
+            eng.set_encoder_kv(encoder_kv)
+        self.tokens = t.zeros(N, self.sample_tokens, dtype=t.long, device=dev)
+        if P:
+            assert (0 <= prime).all() and (prime < ca.bins).all()
+            self.tokens[:, :P] = prime
+        self.get_preds = get_preds
+        if get_preds:
+            self.preds = t.empty(N, self.sample_tokens, ca.bins, dtype=t.float32, device=dev)
+            self.lbuf, self.tstride = self.preds, ca.bins
+        else:
+            self.preds = None
+            self.lbuf, self.tstride = t.empty(N, ca.bins, dtype=t.float32, device=dev), 0
+        self.temp, self.top_k, self.top_p, self.fp16 = temp, top_k, top_p, fp16
+        # the key of this call's Philox stream comes from torch's default generator, so t.manual_seed /
+        # seed_per_rank make sampling reproducible exactly as they do for the reference's Categorical
+        self.seed = int(t.empty((), dtype=t.int64).random_().item())
+        self.pos = 0
+        with t.no_grad():
+            if P > 1 and not get_preds and 1 < P <= eng.prefill_capacity:
+                # the given tokens go through all layers at once (the reference's chunked primed_sample,
+                # autoregressive.py:300-338); chunk_size is moot - one chunk
+                eng.prefill(N, P, tokens=self.tokens, y_cond=self.y_cond, x_cond=self.x_cond)
+                self.pos = P
+
+    def advance(self, upto):
+        """positions [self.pos, upto): given positions are teacher-forced, the others sampled"""
+        upto = min(int(upto), self.sample_tokens)
+        eng, N, P, tokens = self.eng, self.N, self.P, self.tokens
+        with t.no_grad():
+            for sample_t in get_range(range(self.pos, upto)):
+                need = self.get_preds or sample_t >= P
+                eng.step(N, tokens=tokens, y_cond=self.y_cond, x_cond=self.x_cond,
+                         logits=self.lbuf if need else None, logits_tstride=self.tstride)
+                if sample_t >= P:
+                    x = self.preds[:, sample_t] if self.get_preds else self.lbuf
+                    if self.top_k or self.top_p:   # filtering keeps the reference's torch expression (ops.py:113-142)
+                        x = filter_logits(x / self.temp, top_k=self.top_k, top_p=self.top_p).contiguous()
+                        sample_categorical(x, 1.0, self.seed, sample_t, tokens)
+                    else:
+                        sample_categorical(x, self.temp, self.seed, sample_t, tokens)
+        self.pos = max(self.pos, upto)
+
+    def finish(self):
+        assert self.pos == self.sample_tokens, f"window stopped at {self.pos} of {self.sample_tokens}"
+        tr = self.tr
+        with t.no_grad():
+            for b in tr._attn_mods:
+                b.attn._advance(self.N, self.sample_tokens, self.fp16)
+            tr.check_cache(self.N, self.sample_tokens, self.fp16)
+            tr.del_cache()
+            x = self.ca.postprocess(self.tokens, self.sample_tokens)
+        return (x, self.preds) if self.get_preds else x

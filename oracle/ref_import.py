@@ -45,7 +45,11 @@ def load_reference():
         import torch.distributed as dist
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29731")
+            if "MASTER_PORT" not in os.environ:      # any free port: two importers may run side by side
+                import socket
+                with socket.socket() as sk:
+                    sk.bind(("127.0.0.1", 0))
+                    os.environ["MASTER_PORT"] = str(sk.getsockname()[1])
             dist.init_process_group("gloo", rank=0, world_size=1)
         if not torch.cuda.is_available():
             torch.Tensor.cuda = lambda s, *a, **k: s
