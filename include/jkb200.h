@@ -81,6 +81,20 @@ typedef struct jk_layer_weights {
 
 typedef struct jk_prior jk_prior;   /* opaque; lives in the caller's arena */
 
+/* How the engine would lay a configuration out on a device with `n_sms` SMs - pure host arithmetic, no device needed
+ * (the CPU tests use it; the engine itself always plans for the current device).  cols (optional, uint16 pairs
+ * [units][depth][4][2]) receives (first 8-column group, number of groups) of every unit for the four Conv1Ds of a layer. */
+typedef struct jk_prior_plan_info {
+    int32_t k_split;          /* CTAs per unit: they share the unit's columns and split K                 */
+    int32_t units;            /* n_sms / k_split                                                          */
+    int32_t ring_slots;       /* 16 KB weight-ring slots per SM                                           */
+    int32_t smem_bytes;       /* dynamic shared memory of the decode kernel                               */
+    int32_t tile_rows;        /* K/V rows per attention tile                                              */
+    uint64_t arena_bytes;
+    uint64_t stream_stride;   /* bytes of the longest per-SM weight stream (+ padding)                    */
+} jk_prior_plan_info;
+int jk_prior_plan(const jk_prior_config* cfg, int n_sms, jk_prior_plan_info* out, uint16_t* cols, size_t cols_len);
+
 /* bytes of device memory the engine needs for packed weights, KV caches and activations */
 int jk_prior_arena_bytes(const jk_prior_config* cfg, size_t* bytes);
 /* `arena` is device memory (256-B aligned) of at least jk_prior_arena_bytes; it is zeroed here */
@@ -205,6 +219,14 @@ int jk_resblock_cl(const float* x, float* out, float* tmp, const float* w1, cons
 int jk_sample_categorical(const float* logits, int64_t logits_stride, int n, int bins, float temp,
                           uint64_t seed, int position, int64_t* tokens, int64_t tok_stride,
                           jk_stream_t stream);
+
+/* top-k / nucleus filtering in front of the sampler (transformer/ops.py:113-142 `filter_logits`, applied to
+ * logits / temp as autoregressive.py:232-234 does): out[r, v] = logits[r, v] / temp if v stays, else -inf.
+ * top_k > 0: the k largest stay; top_p > 0: the smallest prefix of the sorted row whose softmax mass exceeds top_p
+ * stays (the entry that crosses the threshold included).  Exactly one of the two must be set; bins <= 4096.
+ * Ties at the cut stay together (the reference's scatter-by-index keeps an arbitrary subset of equal values). */
+int jk_filter_logits(const float* logits, int64_t logits_stride, int n, int bins, float temp, int top_k,
+                     float top_p, float* out, int64_t out_stride, jk_stream_t stream);
 
 /* torch Conv1d weight [c_out, c_in, k] (transposed = 0) or ConvTranspose1d weight
  * [c_in, c_out, k] (transposed = 1) -> packed [k, c_in, c_out] */

@@ -29,6 +29,11 @@ class LayerWeights(C.Structure):
                [("w_dtype", C.c_int32), ("b_dtype", C.c_int32)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [("k_split", C.c_int32), ("units", C.c_int32), ("ring_slots", C.c_int32), ("smem_bytes", C.c_int32),
+                ("tile_rows", C.c_int32), ("arena_bytes", C.c_uint64), ("stream_stride", C.c_uint64)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("x_in", C.c_void_p), ("tokens", C.c_void_p),
                 ("tok_stride", C.c_int64), ("y_cond", C.c_void_p), ("x_cond", C.c_void_p),
@@ -57,6 +62,7 @@ SIGNATURES = {
     "jk_last_error": (C.c_char_p, []),
     "jk_version": (_I, []),
     "jk_device_sm_count": (_I, [C.POINTER(C.c_int)]),
+    "jk_prior_plan": (_I, [C.POINTER(PriorConfig), _I, C.POINTER(PlanInfo), _P, C.c_size_t]),
     "jk_prior_arena_bytes": (_I, [C.POINTER(PriorConfig), C.POINTER(C.c_size_t)]),
     "jk_prior_create": (_I, [C.POINTER(PriorConfig), _P, C.c_size_t, C.POINTER(_P), _P]),
     "jk_prior_destroy": (_I, [_P]),
@@ -71,6 +77,7 @@ SIGNATURES = {
     "jk_prior_debug_buffer": (_I, [_P, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "jk_conv1d_prefill_f16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "jk_sample_categorical": (_I, [_P, _L, _I, _I, _F, C.c_uint64, _I, _P, _L, _P]),
+    "jk_filter_logits": (_I, [_P, _L, _I, _I, _F, _I, _F, _P, _L, _P]),
     "jk_vq_argmin": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "jk_vq_gather": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "jk_conv1d_cl": (_I, [C.POINTER(ConvArgs), _P]),

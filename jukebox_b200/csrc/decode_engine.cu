@@ -1515,6 +1515,21 @@ extern "C" int jk_prior_arena_bytes(const jk_prior_config* cfg, size_t* bytes) {
     return 0;
 }
 
+extern "C" int jk_prior_plan(const jk_prior_config* cfg, int n_sms, jk_prior_plan_info* out, uint16_t* cols, size_t cols_len) {
+    JK_REQUIRE(cfg && out, "null argument");
+    JK_REQUIRE(n_sms >= 1 && n_sms <= 1024, "n_sms %d out of range", n_sms);
+    Layout L;
+    int rc = compute_layout(*cfg, n_sms, L);
+    if (rc) return rc;
+    out->k_split = L.KS; out->units = L.U; out->ring_slots = L.nslot; out->smem_bytes = L.smem_bytes; out->tile_rows = L.RC;
+    out->arena_bytes = (uint64_t)L.total; out->stream_stride = (uint64_t)L.stream_stride;
+    if (cols) {
+        JK_REQUIRE(cols_len >= L.cols.size() * 2, "cols buffer too small: %zu < %zu", cols_len, L.cols.size() * 2);
+        for (size_t i = 0; i < L.cols.size(); ++i) { cols[2 * i] = L.cols[i].x; cols[2 * i + 1] = L.cols[i].y; }
+    }
+    return 0;
+}
+
 extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t arena_bytes, jk_prior** out,
                                jk_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -120,6 +120,89 @@ sample_categorical_kernel(const float* __restrict__ logits, long long lstride, i
     }
 }
 
+
+// ---- top-k / nucleus filtering (reference transformer/ops.py:113-142) -----------------------------------
+// out = logits / temp with every entry outside the kept set replaced by -inf.  One CTA per row: the row is sorted
+// (descending, bitonic, shared memory) and the kept set is "values >= cutoff":
+//   top_k : cutoff = k-th largest value (ops.py:125-128: logits < topk(logits, k)[..., -1:] are removed)
+//   top_p : sorted index j is removed iff the softmax mass of sorted[0 .. j-1] exceeds top_p (ops.py:130-140: the
+//           removal mask is shifted right by one, the largest entry always stays); cutoff = last kept value
+constexpr int kFilterMax = 4096;
+
+__global__ void __launch_bounds__(kThreads)
+filter_logits_kernel(const float* __restrict__ logits, long long lstride, int bins, float temp, int top_k, float top_p,
+                     float* __restrict__ out, long long ostride) {
+    __shared__ float s[kFilterMax];
+    __shared__ float s_scan[kThreads / 32];
+    __shared__ int s_keep;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* l = logits + (long long)row * lstride;
+    int P = 1;
+    while (P < bins) P <<= 1;
+    for (int i = tid; i < P; i += kThreads) s[i] = (i < bins) ? __ldcg(l + i) / temp : -INFINITY;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += kThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float a = s[i], b = s[ixj];
+                    const bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float cutoff;
+    if (top_k > 0) {
+        cutoff = s[min(top_k, bins) - 1];
+    } else {
+        // exclusive softmax mass in front of each sorted entry; each thread owns a contiguous run
+        const int per = P / kThreads > 0 ? P / kThreads : 1;
+        const int b0 = tid * per;
+        const float mx = s[0];
+        float local = 0.f;
+        for (int j = 0; j < per; ++j) {
+            const int i = b0 + j;
+            if (i < P) local += (s[i] == -INFINITY) ? 0.f : __expf(s[i] - mx);
+        }
+        float incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        if (tid == 0) s_keep = 1;
+        __syncthreads();
+        float woff = 0.f, total = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            if (w < warp) woff += s_scan[w];
+            total += s_scan[w];
+        }
+        float run = incl + woff - local;                       // mass strictly before b0
+        int keep = 0;                                          // entries of this run that stay
+        for (int j = 0; j < per; ++j) {
+            const int i = b0 + j;
+            if (i < bins) {
+                if (i == 0 || !(run / total > top_p)) keep = i + 1;
+                run += (s[i] == -INFINITY) ? 0.f : __expf(s[i] - mx);
+            }
+        }
+        // the kept set is a prefix (mass is monotone): its length is the largest keep over the threads
+        if (keep > 0) atomicMax(&s_keep, keep);
+        __syncthreads();
+        cutoff = s[s_keep - 1];
+    }
+    float* o = out + (long long)row * ostride;
+    for (int i = tid; i < bins; i += kThreads) {
+        const float v = __ldcg(l + i) / temp;
+        o[i] = (v < cutoff) ? -INFINITY : v;
+    }
+}
+
 }  // namespace
 
 extern "C" int jk_sample_categorical(const float* logits, int64_t logits_stride, int n, int bins, float temp,
@@ -141,6 +224,21 @@ extern "C" int jk_sample_categorical(const float* logits, int64_t logits_stride,
     else if (per <= 16) JK_LAUNCH(16);
     else JK_LAUNCH(32);
 #undef JK_LAUNCH
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int jk_filter_logits(const float* logits, int64_t logits_stride, int n, int bins, float temp, int top_k,
+                                float top_p, float* out, int64_t out_stride, jk_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    JK_REQUIRE(logits && out, "null argument");
+    JK_REQUIRE(bins >= 1 && bins <= kFilterMax, "bins must be in [1, %d]", kFilterMax);
+    JK_REQUIRE(temp > 0.f, "temp must be positive");
+    JK_REQUIRE(top_k >= 0 && top_p >= 0.f && top_p <= 1.f, "top_k >= 0 and 0 <= top_p <= 1 expected");
+    JK_REQUIRE((top_k == 0) != (top_p == 0.f), "exactly one of top_k / top_p must be set (ops.py:122)");
+    if (n == 0) return 0;
+    filter_logits_kernel<<<n, kThreads, 0, stream>>>(logits, (long long)logits_stride, bins, temp, top_k, top_p, out,
+                                                     (long long)out_stride);
     JK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

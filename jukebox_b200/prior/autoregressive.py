@@ -12,7 +12,7 @@ import numpy as np
 import torch as t
 import torch.nn as nn
 
-from ..transformer.ops import filter_logits, sample_categorical
+from ..transformer.ops import filter_logits_scaled, sample_categorical
 from ..transformer.transformer import Transformer
 from ..utils.logger import get_range
 
@@ -223,6 +223,7 @@ class SamplingWindow:
         # seed_per_rank make sampling reproducible exactly as they do for the reference's Categorical
         self.seed = int(t.empty((), dtype=t.int64).random_().item())
         self.pos = 0
+        self.fbuf = None
         with t.no_grad():
             if P > 1 and not get_preds and 1 < P <= eng.prefill_capacity:
                 # the given tokens go through all layers at once (the reference's chunked primed_sample,
@@ -241,9 +242,9 @@ class SamplingWindow:
                          logits=self.lbuf if need else None, logits_tstride=self.tstride)
                 if sample_t >= P:
                     x = self.preds[:, sample_t] if self.get_preds else self.lbuf
-                    if self.top_k or self.top_p:   # filtering keeps the reference's torch expression (ops.py:113-142)
-                        x = filter_logits(x / self.temp, top_k=self.top_k, top_p=self.top_p).contiguous()
-                        sample_categorical(x, 1.0, self.seed, sample_t, tokens)
+                    if self.top_k or self.top_p:   # x / temp -> top-k / nucleus filter (ops.py:113-142): one launch
+                        self.fbuf = filter_logits_scaled(x, self.temp, self.top_k, self.top_p, self.fbuf)
+                        sample_categorical(self.fbuf, 1.0, self.seed, sample_t, tokens)
                     else:
                         sample_categorical(x, self.temp, self.seed, sample_t, tokens)
         self.pos = max(self.pos, upto)

@@ -46,6 +46,8 @@ class Conditioner(nn.Module):
 
 
 class SimpleEmbedding(nn.Module):
+    """one table row per integer label (artist id, genre id)"""
+
     def __init__(self, bins, out_width, init_scale):
         super().__init__()
         self.bins = bins
@@ -53,14 +55,16 @@ class SimpleEmbedding(nn.Module):
         nn.init.normal_(self.emb.weight, std=0.01 * init_scale)
 
     def forward(self, y):
-        assert len(y.shape) == 2, f"Expected shape with 2 dims, got {y.shape}"
-        assert y.dtype == t.long
+        assert y.dim() == 2 and y.dtype == t.long, f"expected a [N, k] LongTensor, got {tuple(y.shape)} {y.dtype}"
+        lo, hi = int(y.min()), int(y.max())
+        assert 0 <= lo and hi < self.bins, f"label ids must lie in [0, {self.bins}), got [{lo}, {hi}]"
         return _embed(y, self.emb.weight)
 
 
 class RangeEmbedding(nn.Module):
-    """positions in [pos_min, pos_max) binned into `bins` embeddings; with n_time > 1 the positions are
-    interpolated between pos_start and pos_end (reference conditioners.py:70-111)."""
+    """A scalar position in [lo, hi) -> one of `bins` table rows (equal-width bins, right-open).  With n_time > 1
+    the module embeds a whole window at once: n_time positions evenly spaced from pos_start towards pos_end
+    (pos_end itself excluded), one row each - the timing signal of the top-level prior."""
 
     def __init__(self, n_time, bins, range, out_width, init_scale, clamp=False):
         super().__init__()
@@ -70,55 +74,76 @@ class RangeEmbedding(nn.Module):
         self.pos_min, self.pos_max = range
         self.clamp = clamp
 
-    def forward(self, pos_start, pos_end=None):
-        assert len(pos_start.shape) == 2
-        pos_start = pos_start.float()
-        if pos_end is not None:
+    def _check(self, pos, name, closed_right):
+        assert pos.dim() == 2, f"{name}: expected [N, 1], got {tuple(pos.shape)}"
+        lo, hi = float(pos.min()), float(pos.max())
+        ok = self.pos_min <= lo and (hi <= self.pos_max if closed_right else hi < self.pos_max)
+        assert ok, f"{name} outside [{self.pos_min}, {self.pos_max}{']' if closed_right else ')'}: [{lo}, {hi}]"
+
+    def bin_ids(self, pos_start, pos_end=None):
+        self._check(pos_start, "pos_start", closed_right=False)
+        first = pos_start.float()
+        if self.n_time == 1:
+            where = first
+        else:
+            assert pos_end is not None, "a window needs its end position"
             if self.clamp:
                 pos_end = pos_end.clamp(self.pos_min, self.pos_max)
-            pos_end = pos_end.float()
-        if self.n_time != 1:
-            assert pos_end is not None
-            interp = t.arange(0, self.n_time, dtype=t.float, device=pos_start.device).view(1, self.n_time) / self.n_time
-            position = pos_start + (pos_end - pos_start) * interp
-        else:
-            position = pos_start
-        norm = (position - self.pos_min) / (self.pos_max - self.pos_min)
-        bins = (self.bins * norm).floor().long().detach()
-        return _embed(bins, self.emb.weight)
+            self._check(pos_end, "pos_end", closed_right=True)
+            frac = t.arange(0, self.n_time, dtype=t.float, device=first.device).view(1, self.n_time) / self.n_time
+            where = first + (pos_end.float() - first) * frac
+        unit = (where - self.pos_min) / (self.pos_max - self.pos_min)          # [0, 1)
+        return (self.bins * unit).floor().long()
+
+    def forward(self, pos_start, pos_end=None):
+        return _embed(self.bin_ids(pos_start, pos_end).detach(), self.emb.weight)
 
 
 class LabelConditioner(nn.Module):
+    """Label rows y = [total_length, offset, length, artist, genre_0 .. genre_{k-1}] (raw-sample units, genre slots
+    padded with -1) -> (start embedding [N, 1, W] = artist + bag of genres, timing embedding [N, n_time, W] or None)."""
+
+    COL_TOTAL, COL_OFFSET, COL_LENGTH, COL_ARTIST, COL_GENRE0 = 0, 1, 2, 3, 4
+
     def __init__(self, y_bins, t_bins, sr, min_duration, max_duration, n_time, out_width, init_scale,
                  max_bow_genre_size, include_time_signal):
         super().__init__()
         self.n_time, self.out_width = n_time, out_width
         assert len(y_bins) == 2, f"Expecting (genre, artist) bins, got {y_bins}"
-        bow_genre_bins, artist_bins = y_bins
+        n_genres, n_artists = y_bins
         self.max_bow_genre_size = max_bow_genre_size
-        self.bow_genre_emb = SimpleEmbedding(bow_genre_bins, out_width, init_scale)
-        self.artist_emb = SimpleEmbedding(artist_bins, out_width, init_scale)
+        self.bow_genre_emb = SimpleEmbedding(n_genres, out_width, init_scale)
+        self.artist_emb = SimpleEmbedding(n_artists, out_width, init_scale)
         self.include_time_signal = include_time_signal
         if include_time_signal:
-            self.total_length_emb = RangeEmbedding(1, t_bins, (min_duration * sr, max_duration * sr), out_width, init_scale)
-            self.absolute_pos_emb = RangeEmbedding(n_time, t_bins, (0.0, max_duration * sr), out_width, init_scale)
+            longest = max_duration * sr
+            self.total_length_emb = RangeEmbedding(1, t_bins, (min_duration * sr, longest), out_width, init_scale)
+            self.absolute_pos_emb = RangeEmbedding(n_time, t_bins, (0.0, longest), out_width, init_scale)
             self.relative_pos_emb = RangeEmbedding(n_time, t_bins, (0.0, 1.0), out_width, init_scale, clamp=True)
 
+    def start_embedding(self, y):
+        artist = self.artist_emb(y[:, self.COL_ARTIST:self.COL_ARTIST + 1])
+        genres = y[:, self.COL_GENRE0:]
+        present = (genres >= 0).float().unsqueeze(2)            # empty genre slots are -1
+        bag = (self.bow_genre_emb(genres.clamp(0)) * present).sum(dim=1, keepdim=True)
+        return bag + artist
+
+    def timing_embedding(self, y):
+        total = y[:, self.COL_TOTAL:self.COL_TOTAL + 1].float()
+        begin = y[:, self.COL_OFFSET:self.COL_OFFSET + 1]
+        finish = (begin + y[:, self.COL_LENGTH:self.COL_LENGTH + 1]).float()
+        begin = begin.float()
+        return self.total_length_emb(total) + self.absolute_pos_emb(begin, finish) + \
+            self.relative_pos_emb(begin / total, finish / total)
+
     def forward(self, y):
-        assert len(y.shape) == 2 and y.shape[-1] == 4 + self.max_bow_genre_size, f"bad label shape {y.shape}"
+        assert y.dim() == 2 and y.shape[-1] == 4 + self.max_bow_genre_size, f"bad label shape {tuple(y.shape)}"
         assert y.dtype == t.long
         N = y.shape[0]
-        total_length, offset, length, artist, genre = y[:, 0:1], y[:, 1:2], y[:, 2:3], y[:, 3:4], y[:, 4:]
-        artist_emb = self.artist_emb(artist)
-        mask = (genre >= 0).float().unsqueeze(2)          # empty genre slots are -1
-        genre_emb = (self.bow_genre_emb(genre.clamp(0)) * mask).sum(dim=1, keepdim=True)
-        start_emb = genre_emb + artist_emb
-        assert_shape(start_emb, (N, 1, self.out_width))
-        pos_emb = None
+        start = self.start_embedding(y)
+        assert_shape(start, (N, 1, self.out_width))
+        timing = None
         if self.include_time_signal:
-            start, end = offset, offset + length
-            total_length, start, end = total_length.float(), start.float(), end.float()
-            pos_emb = self.total_length_emb(total_length) + self.absolute_pos_emb(start, end) + \
-                self.relative_pos_emb(start / total_length, end / total_length)
-            assert_shape(pos_emb, (N, self.n_time, self.out_width))
-        return start_emb, pos_emb
+            timing = self.timing_embedding(y)
+            assert_shape(timing, (N, self.n_time, self.out_width))
+        return start, timing

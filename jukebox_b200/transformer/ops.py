@@ -57,9 +57,9 @@ def _convert_conv_weights_to_fp32(l):
 
 
 def filter_logits(logits, top_k=0, top_p=0.0, filter_value=-float('Inf')):
-    """top-k / nucleus filtering of a logits tensor, semantics of the reference's
-    ops.py:113-142 (stays in torch on purpose: parity is defined on the logits, and the
-    sampling RNG stream is torch's)."""
+    """top-k / nucleus filtering of a logits tensor as a torch expression, semantics of the reference's
+    ops.py:113-142.  The sampling loop uses the one-launch `filter_logits_scaled` below; this form stays for
+    callers that hold arbitrary-shaped logits and as the checker of that kernel in the GPU tests."""
     out = logits.clone()
     top_k = min(top_k, out.size(-1))
     assert (top_k == 0) or (top_p == 0.0)
@@ -74,6 +74,24 @@ def filter_logits(logits, top_k=0, top_p=0.0, filter_value=-float('Inf')):
         drop[..., 0] = 0
         mask = t.zeros_like(out, dtype=t.bool).scatter_(dim=-1, index=order, src=drop)
         out[mask] = filter_value
+    return out
+
+
+def filter_logits_scaled(logits, temp, top_k, top_p, out=None):
+    """filter_logits(logits / temp, top_k, top_p) in ONE launch (jk_filter_logits): the sampling loop's
+    `x = x / temp; x = filter_logits(x, top_k, top_p)` (reference autoregressive.py:232-234).  logits: fp32 CUDA [N, bins]
+    with unit inner stride; returns fp32 [N, bins] (written into `out` when given)."""
+    from .._lib import lib, check, stream_ptr
+    import ctypes as C
+    assert logits.dtype == t.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    if not logits.is_cuda:
+        raise RuntimeError("filter_logits_scaled needs CUDA tensors (no CPU path)")
+    if out is None:
+        out = t.empty(logits.shape, dtype=t.float32, device=logits.device)
+    assert out.shape == logits.shape and out.dtype == t.float32 and out.stride(1) == 1
+    check(lib().jk_filter_logits(C.c_void_p(logits.data_ptr()), logits.stride(0), logits.shape[0], logits.shape[1],
+                                 float(temp), int(top_k), float(top_p), C.c_void_p(out.data_ptr()), out.stride(0),
+                                 stream_ptr()))
     return out
 
 

@@ -92,3 +92,21 @@ def test_low_temperature_is_argmax_and_seed_reproducible():
     b = _draw(logits, 1.0, 11, list(range(32)))
     c = _draw(logits, 1.0, 12, list(range(32)))
     assert (a == b).all() and (a != c).any()
+
+
+@pytest.mark.parametrize("bins", [79, 2048, 2127])
+def test_device_filter_matches_torch_expression(bins):
+    """jk_filter_logits against the torch restatement of the reference's filter_logits (ops.py:113-142)"""
+    from jukebox_b200.transformer.ops import filter_logits, filter_logits_scaled
+    g = torch.Generator(device="cuda").manual_seed(bins)
+    logits = torch.randn(16, bins, device="cuda", generator=g) * 3
+    for temp, top_k, top_p in [(1.0, 5, 0.0), (0.9, 1, 0.0), (0.8, bins + 7, 0.0), (1.0, 0, 0.9), (0.7, 0, 0.3), (1.2, 0, 0.999)]:
+        want = filter_logits(logits / temp, top_k=top_k, top_p=top_p)
+        got = filter_logits_scaled(logits, temp, top_k, top_p)
+        kept_w, kept_g = torch.isfinite(want), torch.isfinite(got)
+        # the kept sets agree except possibly one boundary entry per row under top_p (fp32 cumsum order)
+        diff = (kept_w != kept_g).sum(1)
+        assert int(diff.max()) <= (1 if top_p else 0), (temp, top_k, top_p, diff.tolist())
+        both = kept_w & kept_g
+        assert torch.equal(want[both], got[both])
+        assert bool(kept_g.any(1).all())

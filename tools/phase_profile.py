@@ -21,18 +21,21 @@ def main():
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--pos", type=int, default=4000)
     ap.add_argument("--n", type=int, default=16)
+    ap.add_argument("--workload", default="1b_lyrics")
     args = ap.parse_args()
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
-        prior = bench.build_prior(args.small)
+        prior, _ = bench.build_prior(bench.SMALL if args.small else bench.WORKLOADS[args.workload])
     n = args.n
     ca = prior.prior
     eng = ca._engine(n)
     L = ca.input_dims
     toks = torch.randint(0, ca.bins, (n, L), device="cuda")
     lbuf = torch.empty(n, ca.bins, device="cuda")
-    yc = torch.randn(n, ca.width, device="cuda")
-    xc = torch.zeros(n, 1, ca.width, device="cuda")
+    yc = torch.randn(n, ca.width, device="cuda") if ca.y_cond else None
+    xc = torch.zeros(n, 1, ca.width, device="cuda") if ca.x_cond else None
+    if ca.transformer.encoder_dims:
+        eng.set_encoder_kv(torch.randn(n, ca.transformer.encoder_dims, ca.width, device="cuda"))
     depth = ca.transformer.n_depth
     funcs = [l.attn_func for l in ca.transformer._attn_mods]
     pos = min(args.pos, L - 8)
@@ -57,33 +60,34 @@ def main():
         print(f"     attention attn_func {f}: mean {per[sel, 1].mean():7.2f} us over {len(sel)} layers")
     print(f"  logits + tail        : {d[1 + 5 * depth]:8.2f} us")
     print(f"  per layer            : {per.sum(1).mean():8.2f} us")
-    # intra-phase stamps of CTA 0 (SM clock cycles): slot = index of the barrier that precedes the phase
+    # intra-phase stamps of CTA 0 (SM clock cycles): slot = phase index
     p2 = eng.debug_buffer(6).view(torch.int64).cpu().numpy().reshape(-1, 8).astype(np.float64)
     mhz = 1965.0
-    print("  CTA 0, GEMM phases (us): stage | mma+weights | reduce+epilogue | arrive->barrier-exit")
+    print("  CTA 0, GEMM phases (us): wait+stage | mma+weights | reduce+publish partials | exchange+epilogue")
     for j, nm in ((0, "LN+QKV"), (2, "proj"), (3, "LN+FC"), (4, "proj2")):
         rows = []
         for l in range(depth):
             slot = 1 + 5 * l + j
-            s0, s1, s2, s3, s4, s5 = p2[slot, :6]
-            rows.append([(s1 - s0), (s2 - s1), (s3 - s2), (s5 - s4), p2[slot, 6]])
+            s0, s1, s2, s3, s4 = p2[slot, :5]
+            rows.append([(s1 - s0), (s2 - s1), (s3 - s2), (s4 - s3)])
         r = np.mean(rows, 0) / mhz
-        print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}   (of the mma time, waiting on the weight ring: {r[4]:5.2f} us)")
-    att = np.mean([(p2[1 + 5 * l + 1, 5] - p2[1 + 5 * l + 1, 4]) for l in range(depth)]) / mhz
-    attw = np.mean([(p2[1 + 5 * l + 1, 4] - p2[1 + 5 * l, 5]) for l in range(depth)]) / mhz
-    print(f"     attention (CTA 0): work {attw:6.2f} us, then waits {att:6.2f} us in the barrier")
-    ar = np.array([[p2[1 + 5 * l + 1, i] for i in (0, 1, 2, 3, 6, 4)] for l in range(depth) if funcs[l] in (1, 3)]) / mhz
-    d_ = np.diff(ar, axis=1).mean(0)
-    print(f"     attention block/prev layers, CTA 0 (us): load+sync {d_[0]:5.2f} | scores {d_[1]:5.2f} | softmax+PV {d_[2]:5.2f} | publish+merge {d_[3]:5.2f} | to barrier {d_[4]:5.2f}")
+        print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}")
+    sel = [l for l in range(depth) if funcs[l] in (1, 3) and p2[1 + 5 * l + 1, 3] > 0]
+    if sel:
+        ar = np.array([[p2[1 + 5 * l + 1, i] for i in (0, 1, 2, 3)] for l in sel]) / mhz
+        d_ = np.diff(ar, axis=1).mean(0)
+        print(f"     attention block/prev layers, CTA 0 (us): q/k/v poll + tile load {d_[0]:5.2f} | scores {d_[1]:5.2f} | softmax+PV {d_[2]:5.2f}")
     p3 = eng.debug_buffer(7).view(torch.int64).cpu().numpy().reshape(5, 256, 2).astype(np.float64)
     G = torch.cuda.get_device_properties(0).multi_processor_count
-    print("  layer 1, all CTAs (globaltimer, us): arrival spread min/median/max after the first arrival; exit - last arrival")
+    print("  layer 1, all CTAs (globaltimer, us): phase entry spread (min/median/max after the first entry) | time in phase (min/median/max)")
     for j, nm in enumerate(["LN+QKV", "attention", "proj", "LN+FC", "proj2"]):
         arr, ex = p3[j, :G, 0], p3[j, :G, 1]
         a0 = arr.min()
-        order = np.argsort(arr)
-        print(f"     {nm:10s}: arrivals {0:5.2f} / {np.median(arr - a0) / 1e3:5.2f} / {(arr.max() - a0) / 1e3:5.2f}   "
-              f"exit-last_arrival {np.median(ex - arr.max()) / 1e3:5.2f}   slowest CTAs {order[-4:].tolist()} fastest {order[:3].tolist()}")
+        dur = (ex - arr) / 1e3
+        order = np.argsort(ex)
+        print(f"     {nm:10s}: entry {0:5.2f} / {np.median(arr - a0) / 1e3:5.2f} / {(arr.max() - a0) / 1e3:5.2f}   "
+              f"in phase {dur.min():5.2f} / {np.median(dur):5.2f} / {dur.max():5.2f}   last out {order[-4:].tolist()}")
+    print(f"  layer 1 wall (first entry of LN+QKV -> last exit of proj2): {(p3[4, :G, 1].max() - p3[0, :G, 0].min()) / 1e3:6.2f} us")
 
 
 if __name__ == "__main__":

@@ -10,15 +10,18 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 with contextlib.redirect_stdout(sys.stderr):
-    prior = bench.build_prior("--small" in sys.argv)
+    wl = bench.SMALL if "--small" in sys.argv else bench.WORKLOADS[os.environ.get("JK_WORKLOAD", "1b_lyrics")]
+    prior, _ = bench.build_prior(wl)
 ca = prior.prior
-n = 16
+n = int(os.environ.get("JK_N", "16"))
 eng = ca._engine(n)
 L = ca.input_dims
 toks = torch.randint(0, ca.bins, (n, L), device="cuda")
 lbuf = torch.empty(n, ca.bins, device="cuda")
-yc = torch.randn(n, ca.width, device="cuda")
-xc = torch.zeros(n, 1, ca.width, device="cuda")
+yc = torch.randn(n, ca.width, device="cuda") if ca.y_cond else None
+xc = torch.zeros(n, 1, ca.width, device="cuda") if ca.x_cond else None
+if ca.transformer.encoder_dims:
+    eng.set_encoder_kv(torch.randn(n, ca.transformer.encoder_dims, ca.width, device="cuda"))
 for pos in (500, 4000, 8000):
     pos = min(pos, L - 60)
     eng.reset(pos)
