@@ -210,6 +210,13 @@ int jk_resblock_cl(const float* x, float* out, float* tmp, const float* w1, cons
                    const float* b2, int n, int64_t T, int C, int Cs, int dilation, float res_scale,
                    jk_stream_t stream);
 
+/* The same ResConv1DBlock on the tensor cores for the DECODER side (Decoder stacks of vqvae/encdec.py:87-131 and the
+ * upsampler Conditioner, prior/conditioners.py:8-48), C == Cs in {32, 64}: 3xTF32 split (hi/lo operands, fp32 accumulate in
+ * mma.sync m16n8k8), i.e. fp32 accuracy up to the 2^-22 lo.lo term but NOT the FMA order of jk_resblock_cl.  The encoder,
+ * whose output feeds the bit-exact codebook argmin, must keep jk_resblock_cl. */
+int jk_resblock_tc(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
+                   int n, int64_t T, int C, int dilation, float res_scale, jk_stream_t stream);
+
 /* Token sampling of the autoregressive loop (prior/autoregressive.py:233-235, 343-345):
  *   tokens[r, position] ~ Categorical(logits = logits[r, :] / temp),  r = 0..n-1
  * one launch per position.  logits: fp32 rows `logits_stride` floats apart (entries of -inf carry no

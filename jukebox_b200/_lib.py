@@ -82,6 +82,7 @@ SIGNATURES = {
     "jk_vq_gather": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "jk_conv1d_cl": (_I, [C.POINTER(ConvArgs), _P]),
     "jk_resblock_cl": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _F, _P]),
+    "jk_resblock_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P]),
     "jk_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "jk_layernorm_f32": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "jk_embedding_f32": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),

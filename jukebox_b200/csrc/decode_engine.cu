@@ -55,10 +55,15 @@ constexpr int kMaxSlots = 12;
 constexpr int kHeaderBytes = 8192;     // barriers, LN statistics, descriptor / layer records, residual slice
 constexpr int kLogitKT = 1024;         // K tile (floats) of the fp32 logits product
 constexpr int kLogitRowsPerChunk = 4;
-constexpr int kLogitRowsPerPass = 8;
+constexpr int kLogitRowsPerPass = 16;
 constexpr int kMaxSplit = 8;
 constexpr int kProfSlots = 1024;
 constexpr int kXpCols = 64;            // columns per unit in the partial-sum exchange (8 groups of 8)
+constexpr int kRedBytes = 8 * 16 * 72 * 4;   // cross-warp reduction tile [8 warps][16 rows][<= 72 floats]
+// LayerNorm statistics words: [63:52] number of CTAs that have contributed, [51:0] fixed-point value
+constexpr int kCntShift = 52;
+constexpr unsigned long long kValMask = (1ull << kCntShift) - 1;
+constexpr long long kSumBias = 1ll << 41;      // per contribution, keeps the sum field non-negative
 
 struct StepArgs {
     int n;
@@ -147,10 +152,12 @@ __device__ __forceinline__ uint32_t ll_wait1(const unsigned long long* p, uint32
     while (!ll_ok(w, flag)) { spin_guard(spins); w = ll_ld1(p); }
     return (uint32_t)w;
 }
-// acquire of an arrival counter (wrap-safe comparison)
-__device__ __forceinline__ void wait_counter(const unsigned* cnt, unsigned target) {
+// a statistics word whose count field says every CTA has contributed
+__device__ __forceinline__ unsigned long long wait_stat_word(const long long* p, int G) {
     unsigned spins = 0;
-    while ((int)(ld_acquire_u32(cnt) - target) < 0) spin_guard(spins);
+    unsigned long long w = ll_ld1(reinterpret_cast<const unsigned long long*>(p));
+    while ((int)(w >> kCntShift) != G) { spin_guard(spins); w = ll_ld1(reinterpret_cast<const unsigned long long*>(p)); }
+    return w;
 }
 
 __device__ __forceinline__ float ld_half_cg(const __half* p) {
@@ -166,35 +173,37 @@ __device__ __forceinline__ float quick_gelu_f(float x) {
 }
 
 // ---------------------------------------------------------------------------------------
-// LayerNorm statistics travel with the activations: whoever WRITES columns of the residual
-// stream also adds sum(x) and sum(x^2) of its columns into per-row 64-bit fixed-point accumulators
-// (exact integer adds => order independent => bit-reproducible), so the consuming GEMM can
-// normalise while it stages - no extra passes over the row.
-//   sum  : x * 2^24 is an exact integer for every fp16 value
-//   sumsq: x^2 is exact in fp32; scaled by 2^16 and rounded per element (a pure function of x)
+// LayerNorm statistics travel with the activations: whoever WRITES columns of the residual stream also adds
+// sum(x) and sum(x^2) of its columns into per-row 64-bit fixed-point accumulators (integer adds => order
+// independent => bit-reproducible), so the consuming GEMM can normalise while it stages - no extra pass over
+// the row.  The SAME word counts contributors in its top 12 bits: every CTA adds exactly once per LayerNorm
+// (CTAs without columns add an empty contribution), so "count == G" means the value is complete and the
+// consumer simply polls the word - one red and one poll, no separate counter, no fence.
+//   sum  : x rounded to 2^-16 per element (a pure function of x), biased by 2^41 per contribution
+//   sumsq: min(x^2, 2^24) rounded to 2^-14 per element
+// Worst case (8192 columns at the fp16 maximum) stays below 2^52, so the count field cannot be corrupted.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ long long fx_sum(float x) { return __float2ll_rn(x * 16777216.0f); }
-__device__ __forceinline__ long long fx_sq(float x) { return __float2ll_rn(x * x * 65536.0f); }
-__device__ __forceinline__ void red_add_s64(long long* p, long long v) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+__device__ __forceinline__ long long fx_sum(float x) { return __float2ll_rn(x * 65536.0f); }
+__device__ __forceinline__ long long fx_sq(float x) { return __float2ll_rn(fminf(x * x, 16777216.0f) * 16384.0f); }
+__device__ __forceinline__ void red_add_u64(long long* p, unsigned long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), v);
 }
+__device__ __forceinline__ long long* sm_sfx() { return reinterpret_cast<long long*>(sm_uni() + kRedBytes); }
 
-// This CTA's statistics contribution + arrival.  sfx: [2][n_el] fixed-point values of the elements it wrote,
-// element e belongs to row e / ppc.  32 threads each reduce one (row, moment) in a fixed order, one 64-bit red
-// each; then ONE release-add of the arrival counter (the CTA barrier in front makes it cumulative).
-__device__ __forceinline__ void publish_stats(long long* ln_out, unsigned* cnt, int B, int ppc, int n_el) {
+// This CTA's contribution to the statistics block `ln_out` ([16 rows][2 moments], one 128-byte line each).
+// sfx: [2][1024] fixed-point values of the elements it wrote, element e belongs to row e / ppc.  32 threads each
+// reduce one (row, moment) in a fixed order and issue ONE 64-bit red carrying value + count.
+__device__ __forceinline__ void publish_stats(long long* ln_out, int B, int ppc) {
     const int tid = threadIdx.x;
     consumer_sync();
-    if (ln_out && ppc > 0 && tid < 2 * B) {
-        const long long* sfx = reinterpret_cast<const long long*>(sm_uni() + 32768) + (tid & 1) * 1024;
+    if (tid < 2 * B) {
+        const long long* sfx = sm_sfx() + (tid & 1) * 1024;
         const int row = tid >> 1;
-        long long s = 0;
+        long long s = (tid & 1) ? 0 : kSumBias;
         for (int i = 0; i < ppc; ++i) s += sfx[row * ppc + i];
-        red_add_s64(ln_out + 16 * tid, s);
+        red_add_u64(ln_out + 16 * tid, (1ull << kCntShift) + (unsigned long long)s);
     }
-    consumer_sync();
-    if (tid == 0) red_release_add(cnt, 1u);
-    (void)n_el;
+    consumer_sync();                       // the scratch is reused by the next phase
 }
 
 // activation staging: LL words of rows [0, B), columns [k0, k0 + Ks) -> shared fp16 [16][Ks+8] (ldmatrix
@@ -203,33 +212,37 @@ __device__ __forceinline__ void publish_stats(long long* ln_out, unsigned* cnt, 
 // once) and walks rows rg, rg + rgc, ...; four rows = eight 16-byte polled loads in flight per batch.
 // Rows >= B are never written: an MMA output row depends only on its own A row, and those outputs are discarded.
 __device__ __noinline__ void stage_acts(const unsigned long long* in, int K, int k0, int Ks, int B, uint32_t flag, int ln,
-                                        const float* gamma, const float* beta, const long long* lnacc,
-                                        const unsigned* cnt, unsigned target) {
+                                        const float* gamma, const float* beta, const long long* lnacc) {
     const int tid = threadIdx.x;
     uint8_t* acts = sm_uni();
     float* stats = sm_stats();
     const int nvec = Ks >> 3;
     const int astride = (Ks + 8) * 2;
     if (ln && tid < 32) {
-        // ONE poller per CTA (148 pollers on the counter's L2 line, not 148 x 16); __syncwarp orders its acquire
-        // before the other lanes' loads of the accumulators
-        if (tid == 0) wait_counter(cnt, target);     // every CTA's statistics have arrived
-        __syncwarp();
-    }
-    if (ln && tid < 16) {
-        float mean = 0.f, rstd = 0.f;
-        if (tid < B) {
-            // double only for the cancellation in E[x^2] - mean^2 (adds / muls; no double div or sqrt:
-            // those are kilobytes of library code in the instruction cache)
-            const double rk = (double)(1.0f / (float)K);    // K is a multiple of 16: exact for powers of two, 1e-7 rel otherwise
-            const double m = (double)__ldcg(lnacc + 16 * (2 * tid)) * (1.0 / 16777216.0) * rk;
-            double var = (double)__ldcg(lnacc + 16 * (2 * tid + 1)) * (1.0 / 65536.0) * rk - m * m;
-            var = var < 0.0 ? 0.0 : var;
-            rstd = 1.0f / sqrtf((float)var + 1e-5f);
-            mean = -(float)m * rstd;                        // staged as x * rstd + (-mean * rstd), then * gamma + beta
+        // lanes 2r / 2r+1 poll the sum / sum-of-squares word of row r until every CTA has contributed
+        const int G = sm_E()->G;
+        long long val = 0;
+        if (tid < 2 * B) {
+            const unsigned long long w = wait_stat_word(lnacc + 16 * tid, G);
+            val = (long long)(w & kValMask) - ((tid & 1) ? 0ll : (long long)G * kSumBias);
         }
-        stats[2 * tid] = mean;
-        stats[2 * tid + 1] = rstd;
+        const long long sq = __shfl_xor_sync(0xffffffffu, val, 1);
+        if (!(tid & 1)) {
+            const int row = tid >> 1;
+            float mean = 0.f, rstd = 0.f;
+            if (row < B) {
+                // double only for the cancellation in E[x^2] - mean^2 (adds / muls; no double div or sqrt:
+                // those are kilobytes of library code in the instruction cache)
+                const double rk = (double)(1.0f / (float)K);    // K is a multiple of 16: exact for powers of two, 1e-7 rel otherwise
+                const double m = (double)val * (1.0 / 65536.0) * rk;
+                double var = (double)sq * (1.0 / 16384.0) * rk - m * m;
+                var = var < 0.0 ? 0.0 : var;
+                rstd = 1.0f / sqrtf((float)var + 1e-5f);
+                mean = -(float)m * rstd;                        // staged as x * rstd + (-mean * rstd), then * gamma + beta
+            }
+            stats[2 * row] = mean;
+            stats[2 * row + 1] = rstd;
+        }
     }
     const int cw = nvec >= kConsumers ? kConsumers : nvec;           // column vectors covered per pass
     const int rgc = nvec >= kConsumers ? 1 : kConsumers / nvec;      // row groups
@@ -310,13 +323,15 @@ __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-// one ring slot worth of k-steps for this warp.  NCG (8-column groups of this unit) is a template
-// parameter: with a run-time count the compiler serialised every LDS -> HMMA pair through one
-// register pair (tools/micro/ubench.cu: 4070 vs 1170 cycles for the K = 2048 loop).
+// one ring slot worth of k-steps, all of it by ONE warp: the slot's k-steps x column groups are independent MMAs
+// that pipeline back to back (round 1 split every slot over the eight warps - one k-step per warp per slot - and
+// paid the mbarrier wait + LDS -> HMMA latency chain once per slot per warp: 1.2 us for four slots).  NCG (8-column
+// groups of this unit) is a template parameter: with a run-time count the compiler serialised every LDS -> HMMA pair
+// through one register pair (tools/micro/ubench.cu: 4070 vs 1170 cycles for the K = 2048 loop).
 template <int NCG>
-__device__ __forceinline__ void mma_chunk(float (&acc)[8][4], uint32_t arow, uint32_t sl, int kk0, int nk, int warp) {
+__device__ __forceinline__ void mma_chunk(float (&acc)[8][4], uint32_t arow, uint32_t sl, int kk0, int nk) {
 #pragma unroll 4
-    for (int i = warp; i < nk; i += 8) {
+    for (int i = 0; i < nk; ++i) {
         uint32_t a[4];
         ldsm4(a, arow + (kk0 + i) * 32);
         uint2 b[NCG];
@@ -341,11 +356,8 @@ struct GemmArgs {
     int K, N, g0, ncg, ln, epi, pslot;
     uint32_t flag_in, flag_out;
     const float *gamma, *beta, *bias;
-    const long long* ln_in;
-    const unsigned* cnt_in;             // arrival counter behind ln_in
-    unsigned target_in;
-    long long* ln_out;                  // statistics of the rows this epilogue writes (residual epilogues)
-    unsigned* cnt_out;                  // arrival counter to add to when done (residual epilogues)
+    const long long* ln_in;             // statistics block behind the input (LayerNorm phases)
+    long long* ln_out;                  // statistics block of the rows this epilogue writes (residual epilogues)
 };
 
 __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
@@ -357,13 +369,13 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     const int ppc = (nc >> 1) / KS;                      // column pairs this CTA finishes
     const bool residual = (g.epi == EPI_PROJ || g.epi == EPI_PROJ2);
     STAMP(E, g.pslot, 0);
-    if (ncg == 0) {                                      // a unit without columns (tiny models) still arrives
-        if (residual) publish_stats(nullptr, g.cnt_out, B, 0, 0);
+    if (ncg == 0) {                                      // a unit without columns (tiny models) still contributes (count only)
+        if (residual) publish_stats(g.ln_out, B, 0);
         return ring;
     }
     const int K = g.K, N = g.N, epi = g.epi;
     const int Ks = K / KS, k0 = rank * Ks;
-    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in, g.cnt_in, g.target_in);
+    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in);
     consumer_sync();
     STAMP(E, g.pslot, 1);
 
@@ -374,37 +386,51 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     const int kpc = kpc_of(ncg);
     const int astride = (Ks + 8) * 2;
     const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
+    // slot s of this Conv1D is multiplied by warp s % 8 alone.  EVERY warp still waits for the slot and arrives on its
+    // empty barrier: the parity protocol of the ring only holds while no warp is a whole ring ahead of or behind the
+    // producer (a warp that skipped the handshake of foreign slots aliased phases once a Conv1D had more slots than
+    // the ring: 38 vs 6 for 5b_lyrics).
 #define JK_MMA_LOOP(NCG)                                                                      \
-    _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                            \
-        const int nk = min(kpc, nkk - kk0);                                                    \
-        mbar_wait(ring.full(), ring.phase);                                                    \
-        mma_chunk<NCG>(acc, arow, smem_u32(ring.data()) + lane * 8, kk0, nk, warp);            \
-        __syncwarp();                                                                          \
-        if (lane == 0) mbar_arrive(ring.empty());                                              \
-        ring.advance();                                                                        \
+    {                                                                                         \
+        int owner = 0;                                                                        \
+        _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                        \
+            mbar_wait(ring.full(), ring.phase);                                                \
+            if (owner == warp) {                                                              \
+                const int nk = min(kpc, nkk - kk0);                                            \
+                mma_chunk<NCG>(acc, arow, smem_u32(ring.data()) + lane * 8, kk0, nk);          \
+            }                                                                                 \
+            __syncwarp();                                                                      \
+            if (lane == 0) mbar_arrive(ring.empty());                                          \
+            owner = (owner + 1) & 7;                                                          \
+            ring.advance();                                                                   \
+        }                                                                                     \
     }
     switch (ncg) {
-        case 1: { JK_MMA_LOOP(1) } break;
-        case 2: { JK_MMA_LOOP(2) } break;
-        case 3: { JK_MMA_LOOP(3) } break;
-        case 4: { JK_MMA_LOOP(4) } break;
-        case 5: { JK_MMA_LOOP(5) } break;
-        case 6: { JK_MMA_LOOP(6) } break;
-        case 7: { JK_MMA_LOOP(7) } break;
-        default: { JK_MMA_LOOP(8) } break;
+        case 1: JK_MMA_LOOP(1) break;
+        case 2: JK_MMA_LOOP(2) break;
+        case 3: JK_MMA_LOOP(3) break;
+        case 4: JK_MMA_LOOP(4) break;
+        case 5: JK_MMA_LOOP(5) break;
+        case 6: JK_MMA_LOOP(6) break;
+        case 7: JK_MMA_LOOP(7) break;
+        default: JK_MMA_LOOP(8) break;
     }
 #undef JK_MMA_LOOP
     STAMP(E, g.pslot, 2);
     consumer_sync();                       // everyone is done reading the staged activations
-    float* red = reinterpret_cast<float*>(uni);   // [8 warps][ncg][16][8]  (<= 32 KB)
-    {
+    // cross-warp reduction tile [warps that owned a slot][16 rows][ncp floats]; ncp = 8 mod 32 keeps both the fragment
+    // stores below and the row-wise pair loads of the epilogue free of bank conflicts
+    float* red = reinterpret_cast<float*>(uni);
+    const int ncp = ((nc + 31) & ~31) + 8;
+    const int nwarp = min(8, (nkk + kpc - 1) / kpc);
+    if (warp < nwarp) {
         const int r0 = lane >> 2, c0 = (lane & 3) * 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j < ncg) {
-                float* d = red + ((warp * ncg + j) * 16) * 8;
-                *reinterpret_cast<float2*>(d + r0 * 8 + c0) = make_float2(acc[j][0], acc[j][1]);
-                *reinterpret_cast<float2*>(d + (r0 + 8) * 8 + c0) = make_float2(acc[j][2], acc[j][3]);
+                float* d = red + (size_t)(warp * 16) * ncp + j * 8 + c0;
+                *reinterpret_cast<float2*>(d + r0 * ncp) = make_float2(acc[j][0], acc[j][1]);
+                *reinterpret_cast<float2*>(d + (r0 + 8) * ncp) = make_float2(acc[j][2], acc[j][3]);
             }
         }
     }
@@ -416,11 +442,9 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
 #pragma unroll 1
         for (int e = tid; e < B * npair; e += kConsumers) {
             const int b = e / npair, pr = e - b * npair;
-            const int j = pr >> 2, col = (pr & 3) * 2;
             float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const float2 v = *reinterpret_cast<const float2*>(red + ((w * ncg + j) * 16 + b) * 8 + col);
+            for (int w = 0; w < nwarp; ++w) {
+                const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
                 s0 += v.x; s1 += v.y;
             }
             unsigned long long* dst = xp_unit + ((size_t)rank * 16 + b) * kXpCols + 2 * pr;
@@ -432,7 +456,7 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     STAMP(E, g.pslot, 3);
     // ---- ... and finishes its own column pairs ----------------------------------------------------------
     float2* res = sm_res();
-    long long* sfx = reinterpret_cast<long long*>(uni + 32768);      // [2][1024] statistics of the elements written
+    long long* sfx = sm_sfx();                                        // [2][1024] statistics of the elements written
     const int n_el = B * ppc;
 #pragma unroll 1
     for (int e = tid; e < n_el; e += kConsumers) {
@@ -442,10 +466,8 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
         const float2 bias = *reinterpret_cast<const float2*>(g.bias + gc);
         float s0 = 0.f, s1 = 0.f;
         if (KS == 1) {
-            const int j = pr >> 2, col = (pr & 3) * 2;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const float2 v = *reinterpret_cast<const float2*>(red + ((w * ncg + j) * 16 + b) * 8 + col);
+            for (int w = 0; w < nwarp; ++w) {
+                const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
                 s0 += v.x; s1 += v.y;
             }
         } else {
@@ -484,7 +506,7 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
         ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
     }
     STAMP(E, g.pslot, 4);
-    if (residual) publish_stats(g.ln_out, g.cnt_out, B, ppc, n_el);
+    if (residual) publish_stats(g.ln_out, B, ppc);
     else consumer_sync();                  // red region is reused by the next phase
     return ring;
 }
@@ -668,7 +690,7 @@ __device__ __noinline__ void attn_merge(int item, int ns, int b, int h, uint32_t
 //   * parts of one (sample, head) are merged by the last CTA to finish (atomic ticket); the output goes to
 //     the `a` LL buffer, which IS the attention -> proj hand-over
 __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int s, int ns,
-                                       const AttnGeom G, int pslot, uint32_t flag) {
+                                       const AttnGeom G, int pslot, uint32_t flag, int pre) {
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     float* stats = sm_stats();
@@ -679,7 +701,9 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     const int swz = (nvec & 7) ? 0 : 7;
     const int RC = E->RC;
     const int tileB = RC * dhp * 2;
-    const uint32_t regA = smem_u32(uni), regB = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes);
+    // two tile regions; a prefetched first tile (attn_prefetch) sits in the second one, which no other phase touches
+    const uint32_t regU = smem_u32(uni), regX = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes);
+    const uint32_t regA = pre ? regX : regU, regB = pre ? regU : regX;
     __half* qh = reinterpret_cast<__half*>(uni + 2 * tileB);          // [dhp] q, then [dhp] k_new, [dhp] v_new
     __half* kn = qh + dhp;
     __half* vn = kn + dhp;
@@ -702,7 +726,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
         kv_copy_tile(kd, vd, kbase + (size_t)r0 * dhp, vbase + (size_t)r0 * dhp, nr, dhp, swz);
     };
     STAMP(E, pslot, 0);
-    if (R > 0) issue_tile(0);               // cached rows do not depend on the current token: load them first
+    if (R > 0 && !pre) issue_tile(0);       // cached rows do not depend on the current token: load them first
     // ---- q, k_new, v_new of this (sample, head): LL words of the QKV Conv1D, polled --------------------------
     {
         const int hw = dhp >> 1, dw = dh >> 1;
@@ -841,6 +865,29 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     consumer_sync();
     if (stats[48] != 0.f) attn_merge(item, ns, b, h, flag);
     STAMP(E, pslot, 6);
+}
+
+// The cached K/V rows of this CTA's first attention item do not depend on the current token: issue their cp.async BEFORE
+// the layer's QKV Conv1D, into the tile region that only the attention phase uses, so that the HBM latency hides behind
+// that phase.  Returns 1 if the tile is on its way.
+__device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t) {
+    const EngineDev* E = sm_E();
+    if (!E->kv_prefetch) return 0;
+    const LayerDev LD = LD_ref;
+    const AttnGeom G = attn_geom(E, LD, t);
+    if (G.R == 0) return 0;
+    const int ncache = G.R - (G.cur ? 1 : 0);
+    const int ns = attn_nsplit(E, B, ncache);
+    if (c >= B * E->H * ns) return 0;
+    const int s = c % ns, bh = c / ns, b = bh / E->H, h = bh % E->H;
+    const int dhp = E->dh_pad, nvec = dhp >> 3, RC = E->RC;
+    const int swz = (nvec & 7) ? 0 : 7;
+    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
+    const int nr = max(0, min(RC - 1, i1 - i0));
+    const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
+    const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + RC * dhp * 2;
+    kv_copy_tile(kd, vd, LD.kc + (cbase + G.base + i0) * dhp, LD.vc + (cbase + G.base + i0) * dhp, nr, dhp, swz);
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1035,10 +1082,19 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     const unsigned step = *reinterpret_cast<volatile const unsigned*>(E->sync + 64);
     const int B = A.n, W = E->W, S = E->S, M = E->M, G = E->G, depth = E->depth;
     const uint32_t fbase = step * (uint32_t)(depth + 2);          // LL flags of this launch: fbase + 1 .. fbase + depth + 1
-    unsigned* cnt0 = E->sync;                                     // arrivals behind LN0 statistics (+ the final h)
-    unsigned* cnt1 = E->sync + 32;                                // arrivals behind LN1 statistics
-    const unsigned cnt0_base = step * (unsigned)(depth + 1) * (unsigned)G;
-    const unsigned cnt1_base = step * (unsigned)depth * (unsigned)G;
+    // statistics blocks: 2l = input of layer l's LN0, 2l + 1 = input of its LN1, 2 * depth = the final residual stream
+    // (nobody normalises it; its count tells CTA 0 that every CTA is through the stack)
+#define LN_BLOCK(i_) (E->lnacc + (size_t)(i_) * 512)
+    // CTA 0 clears a block for the next launch once a LATER block is complete: every CTA contributes to the later block
+    // only after it has consumed the earlier one (program order + data dependence)
+#define CLEAR_AFTER(clear_, seen_)                                                             \
+    do {                                                                                       \
+        if (c == 0 && tid < 32) {                                                              \
+            if (tid == 0) wait_stat_word(LN_BLOCK(seen_), G);                                  \
+            __syncwarp();                                                                      \
+            LN_BLOCK(clear_)[16 * tid] = 0;                                                    \
+        }                                                                                      \
+    } while (0)
     unsigned nph = 0;                                             // phase index (profiling slots)
 #define PHASE_DONE()                                                                           \
     do {                                                                                       \
@@ -1069,7 +1125,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         const ushort2 wc = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 128)[1];     // column groups of width-W outputs
         const int ppc = (wc.y * 4) / KS, n_el = B * ppc;
         float2* res = sm_res();
-        long long* sfx = reinterpret_cast<long long*>(sm_uni() + 32768);
+        long long* sfx = sm_sfx();
         for (int e = tid; e < n_el; e += kConsumers) {
             const int b = e / ppc, pl = e - b * ppc;
             const int col = wc.x * 8 + 2 * (rank * ppc + pl);
@@ -1094,7 +1150,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             sfx[1024 + e] = fx_sq(hv.x) + fx_sq(hv.y);
             ll_st(E->ll_h + (((size_t)b * W + col) >> 1), *reinterpret_cast<const uint32_t*>(&hh), fbase + 1);
         }
-        publish_stats(E->lnacc, cnt0, B, ppc, n_el);
+        publish_stats(LN_BLOCK(0), B, ppc);
     }
     PHASE_DONE();
 
@@ -1104,6 +1160,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
         const uint32_t fl = fbase + (uint32_t)l + 1;              // flag of this layer's buffers
+        const int pre = attn_prefetch(LD, B, c, t);
         // a fresh argument record per phase: nothing of it stays live across the calls in between
         if (l == 1) PROF3(0, 0);
         {
@@ -1111,19 +1168,12 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_h; ga.out = E->ll_qkv; ga.xp = E->xp[0]; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y;
             ga.ln = 1; ga.epi = EPI_QKV; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-            ga.ln_in = E->lnacc + (size_t)(2 * l) * 512; ga.cnt_in = cnt0; ga.target_in = cnt0_base + (unsigned)(l + 1) * (unsigned)G;
-            ga.ln_out = nullptr; ga.cnt_out = nullptr;
+            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(0, 1);
-        // LN1 statistics of the previous layer are consumed once every CTA has arrived behind this layer's LN0 (its
-        // proj2 epilogue follows its FC staging).  CTA 0 normally passed that wait inside the phase above; waiting
-        // again costs one L2 hit and covers a CTA 0 without QKV columns (tiny models).
-        if (c == 0 && tid < 32 && l > 0) {
-            if (tid == 0) wait_counter(cnt0, cnt0_base + (unsigned)(l + 1) * (unsigned)G);
-            __syncwarp();
-            E->lnacc[(size_t)(2 * l - 1) * 512 + 16 * tid] = 0;
-        }
+        // LN1 statistics of the previous layer: consumed once this layer's LN0 block is complete
+        if (l > 0) CLEAR_AFTER(2 * l - 1, 2 * l);
         // next layer's record + column assignment -> the other shared-memory slot.  The descriptor is in
         // HBM (the weight stream evicts it from L2 every step): issue the loads here so their latency hides
         // behind the attention phase instead of sitting on the dependency chain.
@@ -1142,7 +1192,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             const int ns = attn_nsplit(E, B, geo.R - ((geo.R > 0 && geo.cur) ? 1 : 0));
             for (int it = c; it < B * E->H * ns; it += G) {
                 const int s = it % ns, bh = it / ns;
-                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nph, fl);
+                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nph, fl, pre && it == c);
                 consumer_sync();           // tile / q regions are reused by the next item or the next phase
             }
         }
@@ -1153,8 +1203,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             GemmArgs ga;
             ga.in = E->ll_a; ga.out = E->ll_x1; ga.xp = E->xp[1]; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y;
             ga.ln = 0; ga.epi = EPI_PROJ; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
-            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr; ga.cnt_in = nullptr; ga.target_in = 0;
-            ga.ln_out = E->lnacc + (size_t)(2 * l + 1) * 512; ga.cnt_out = cnt1;
+            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
+            ga.ln_out = LN_BLOCK(2 * l + 1);
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(2, 1);
@@ -1165,25 +1215,20 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_x1; ga.out = E->ll_g; ga.xp = E->xp[2]; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y;
             ga.ln = 1; ga.epi = EPI_FC; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-            ga.ln_in = E->lnacc + (size_t)(2 * l + 1) * 512; ga.cnt_in = cnt1; ga.target_in = cnt1_base + (unsigned)(l + 1) * (unsigned)G;
-            ga.ln_out = nullptr; ga.cnt_out = nullptr;
+            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(3, 1);
-        // LN0 statistics of this layer are consumed once every CTA has arrived behind LN1 (proj epilogue follows QKV staging)
-        if (c == 0 && tid < 32) {
-            if (tid == 0) wait_counter(cnt1, cnt1_base + (unsigned)(l + 1) * (unsigned)G);
-            __syncwarp();
-            E->lnacc[(size_t)(2 * l) * 512 + 16 * tid] = 0;
-        }
+        // LN0 statistics of this layer: consumed once its LN1 block is complete
+        CLEAR_AFTER(2 * l, 2 * l + 1);
         PHASE_DONE();
         if (l == 1) PROF3(4, 0);
         {
             GemmArgs ga;
             ga.in = E->ll_g; ga.out = E->ll_h; ga.xp = E->xp[3]; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y;
             ga.ln = 0; ga.epi = EPI_PROJ2; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl + 1;
-            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr; ga.cnt_in = nullptr; ga.target_in = 0;
-            ga.ln_out = (l + 1 < depth) ? E->lnacc + (size_t)(2 * l + 2) * 512 : nullptr; ga.cnt_out = cnt0;
+            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
+            ga.ln_out = LN_BLOCK(2 * l + 2);
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(4, 1);
@@ -1200,12 +1245,11 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         }
     }
     if (do_logits) logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
+    // the last LN1 block and the final block: clear them once every CTA is through the stack
+    CLEAR_AFTER(2 * depth - 1, 2 * depth);
     if (c == 0) {
-        // the last arrival: every CTA is through its last LN1 staging, its statistics can be cleared; then the
-        // bookkeeping of the launch
-        if (tid == 0) wait_counter(cnt0, cnt0_base + (unsigned)(depth + 1) * (unsigned)G);
         consumer_sync();
-        if (tid < 32) E->lnacc[(size_t)(2 * depth - 1) * 512 + 16 * tid] = 0;
+        if (tid < 32) LN_BLOCK(2 * depth)[16 * tid] = 0;
         if (tid == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1214,6 +1258,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             *(E->sync + 64) = step + 1;
         }
     }
+#undef LN_BLOCK
+#undef CLEAR_AFTER
 #undef PHASE_DONE
 #undef PROF3
 }
@@ -1415,7 +1461,7 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     for (;; RC >>= 1) {
         size_t uni = (size_t)act_rows * (Kmax + 8) * 2;
         uni = std::max(uni, (size_t)16 * kLogitKT * 4);
-        uni = std::max(uni, (size_t)32768 + 2 * 1024 * 8);                           // cross-warp reduction + statistics scratch
+        uni = std::max(uni, (size_t)kRedBytes + 2 * 1024 * 8);                       // cross-warp reduction + statistics scratch
         const size_t kv_stage = (size_t)2 * RC * L.dh_pad * 2;                        // one K tile + one V tile
         size_t attn = kv_stage + (size_t)3 * L.dh_pad * 2 + 64 * 4 + (size_t)L.dh_pad * 4 + 64;   // tiles, q/k/v, scores, running output
         uni = std::max(uni, attn);
@@ -1556,6 +1602,7 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
     E.depth = cfg->depth; E.G = G; E.KS = L.KS; E.U = L.U; E.RC = L.RC; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
+    E.kv_prefetch = getenv("JK_KV_PREFETCH") ? atoi(getenv("JK_KV_PREFETCH")) : 1;
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);

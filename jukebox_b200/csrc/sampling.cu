@@ -40,12 +40,14 @@ sample_categorical_kernel(const float* __restrict__ logits, long long lstride, i
     const float* l = logits + (long long)row * lstride;
     const int per = (bins + kThreads - 1) / kThreads;
     const int b0 = tid * per;
+    // x / temp as torch computes it on a GPU for a scalar divisor: x * (1 / temp) (BinaryDivTrueKernel: a * reciprocal(b))
+    const float inv_temp = 1.0f / temp;
     float e[MAX_PER];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAX_PER; ++j) {
         const int b = b0 + j;
-        e[j] = (j < per && b < bins) ? __ldcg(l + b) / temp : -INFINITY;
+        e[j] = (j < per && b < bins) ? __ldcg(l + b) * inv_temp : -INFINITY;
         mx = fmaxf(mx, e[j]);
     }
     mx = jk::warp_max(mx);
@@ -139,7 +141,8 @@ filter_logits_kernel(const float* __restrict__ logits, long long lstride, int bi
     const float* l = logits + (long long)row * lstride;
     int P = 1;
     while (P < bins) P <<= 1;
-    for (int i = tid; i < P; i += kThreads) s[i] = (i < bins) ? __ldcg(l + i) / temp : -INFINITY;
+    const float inv_temp = 1.0f / temp;         // torch's x / scalar on a GPU: x * (1 / scalar)
+    for (int i = tid; i < P; i += kThreads) s[i] = (i < bins) ? __ldcg(l + i) * inv_temp : -INFINITY;
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -198,7 +201,7 @@ filter_logits_kernel(const float* __restrict__ logits, long long lstride, int bi
     }
     float* o = out + (long long)row * ostride;
     for (int i = tid; i < bins; i += kThreads) {
-        const float v = __ldcg(l + i) / temp;
+        const float v = __ldcg(l + i) * inv_temp;
         o[i] = (v < cutoff) ? -INFINITY : v;
     }
 }

@@ -6,6 +6,7 @@
 // arithmetic (no TF32): see DESIGN.md "VQ-VAE numerics".
 #include "common.cuh"
 #include <stdlib.h>
+#include <algorithm>
 #include "../../include/jkb200.h"
 
 using namespace jk;
@@ -428,6 +429,165 @@ int launch_resblock_fused(const float* x, float* out, const float* w1, const flo
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// ResConv1DBlock on the tensor cores, for the DECODER side (Decoder / Conditioner stacks: their outputs are audio and
+// conditioning, never an argmin input, so summation order is free; the encoder keeps the exact-FMA kernel above).
+// fp32 accuracy is kept with the 3xTF32 split: x = hi + lo (both TF32), x.w ~= lo.w_hi + hi.w_lo + hi.w_hi with fp32
+// accumulation in mma.sync.m16n8k8 - only the lo.lo term (2^-22 relative) is dropped.
+//   * persistent CTAs (grid = #SMs): W1 / W2 are split into hi / lo planes in shared memory ONCE per CTA, then the CTA
+//     walks tiles of 64 positions; per tile the three relu'd input tap tiles are staged like in the FMA kernel
+//   * 8 warps = 4 row blocks of 16 positions x 2 halves of the output channels; A fragments come from the tap tiles
+//     (row stride C + 4: the (g, t) lanes of a fragment land in 32 different banks), B fragments from the weight planes
+//     (row stride C + 8: likewise); the hidden tile goes through shared memory between the two convolutions
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int C>
+struct ResTC {
+    static constexpr int TT = 64, XS = C + 4, WS = C + 8, NT = C / 16;
+    static constexpr size_t smem_floats = (size_t)2 * 3 * C * WS + (size_t)2 * C * WS + (size_t)3 * TT * XS + (size_t)TT * XS;
+};
+
+// one k8 step of a warp tile: A fragment (16 positions x 8 channels) from `arow`, NT n-tiles of 8 output channels
+template <int C>
+__device__ __forceinline__ void tc_kstep(float (&acc)[ResTC<C>::NT][4], const float* arow, const float* wh, const float* wl,
+                                         int g, int t4) {
+    constexpr int XS = ResTC<C>::XS, WS = ResTC<C>::WS, NT = ResTC<C>::NT;
+    uint32_t ah[4], al[4];
+    split_tf32(arow[g * XS + t4], ah[0], al[0]);
+    split_tf32(arow[(g + 8) * XS + t4], ah[1], al[1]);
+    split_tf32(arow[g * XS + t4 + 4], ah[2], al[2]);
+    split_tf32(arow[(g + 8) * XS + t4 + 4], ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int o0 = t4 * WS + nt * 8 + g, o1 = (t4 + 4) * WS + nt * 8 + g;
+        const uint32_t bh0 = __float_as_uint(wh[o0]), bh1 = __float_as_uint(wh[o1]);
+        const uint32_t bl0 = __float_as_uint(wl[o0]), bl1 = __float_as_uint(wl[o1]);
+        mma_tf32(acc[nt], al, bh0, bh1);
+        mma_tf32(acc[nt], ah, bl0, bl1);
+        mma_tf32(acc[nt], ah, bh0, bh1);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 1)
+resblock_tc_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w1,
+                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                   long long T, int dil, float rs, long long tiles_per_clip, long long total_tiles) {
+    constexpr int TT = ResTC<C>::TT, XS = ResTC<C>::XS, WS = ResTC<C>::WS, NT = ResTC<C>::NT;
+    extern __shared__ __align__(16) float tsm[];
+    float* w1h = tsm;                       // [3][C][WS]
+    float* w1l = w1h + 3 * C * WS;
+    float* w2h = w1l + 3 * C * WS;          // [C][WS]
+    float* w2l = w2h + C * WS;
+    float* xs = w2l + C * WS;               // [3][TT][XS]  relu(x) at t + (tap - 1) * dil
+    float* hs = xs + 3 * TT * XS;           // [TT][XS]     relu(hidden)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * (C / 2);
+    for (int i = tid; i < 3 * C * C; i += 256) {
+        uint32_t hi, lo;
+        split_tf32(__ldg(w1 + i), hi, lo);
+        const int o = (i / C) * WS + i % C;
+        w1h[o] = __uint_as_float(hi); w1l[o] = __uint_as_float(lo);
+    }
+    for (int i = tid; i < C * C; i += 256) {
+        uint32_t hi, lo;
+        split_tf32(__ldg(w2 + i), hi, lo);
+        const int o = (i / C) * WS + i % C;
+        w2h[o] = __uint_as_float(hi); w2l[o] = __uint_as_float(lo);
+    }
+    constexpr int TX = C / 4;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * TT;
+        const float* xin = x + (size_t)nb * T * C;
+        float* xout = out + (size_t)nb * T * C;
+        __syncthreads();                    // previous tile's readers of xs / hs are done (and the weights are staged)
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+            const long long off = (long long)(tap - 1) * dil;
+#pragma unroll 4
+            for (int i = tid; i < TT * TX; i += 256) {
+                const int tt = i / TX, c4 = i % TX;
+                const long long tp = t0 + tt + off;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tp >= 0 && tp < T) v = __ldg(reinterpret_cast<const float4*>(xin + (size_t)tp * C) + c4);
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                *reinterpret_cast<float4*>(xs + ((size_t)tap * TT + tt) * XS + c4 * 4) = v;
+            }
+        }
+        __syncthreads();
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 1
+        for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll 2
+            for (int k8 = 0; k8 < C / 8; ++k8)
+                tc_kstep<C>(acc, xs + ((size_t)tap * TT + m0) * XS + k8 * 8, w1h + ((size_t)tap * C + k8 * 8) * WS + n0,
+                            w1l + ((size_t)tap * C + k8 * 8) * WS + n0, g, t4);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {   // hidden = relu(conv1 + b1) -> shared memory
+            const int col = n0 + nt * 8 + 2 * t4;
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(b1 + col));
+            *reinterpret_cast<float2*>(hs + (size_t)(m0 + g) * XS + col) = make_float2(fmaxf(acc[nt][0] + bv.x, 0.f), fmaxf(acc[nt][1] + bv.y, 0.f));
+            *reinterpret_cast<float2*>(hs + (size_t)(m0 + g + 8) * XS + col) = make_float2(fmaxf(acc[nt][2] + bv.x, 0.f), fmaxf(acc[nt][3] + bv.y, 0.f));
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k8 = 0; k8 < C / 8; ++k8)
+            tc_kstep<C>(acc, hs + (size_t)m0 * XS + k8 * 8, w2h + (size_t)(k8 * 8) * WS + n0, w2l + (size_t)(k8 * 8) * WS + n0, g, t4);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = n0 + nt * 8 + 2 * t4;
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(b2 + col));
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const long long t = t0 + m0 + g + 8 * hlf;
+                if (t < T) {
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(xin + (size_t)t * C + col));
+                    float2 v;
+                    v.x = rs * (acc[nt][2 * hlf] + bv.x); v.x += r.x;
+                    v.y = rs * (acc[nt][2 * hlf + 1] + bv.y); v.y += r.y;
+                    *reinterpret_cast<float2*>(xout + (size_t)t * C + col) = v;
+                }
+            }
+        }
+    }
+}
+
+template <int C>
+int launch_resblock_tc(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
+                       int n, long long T, int dil, float rs, cudaStream_t stream) {
+    constexpr size_t smem = ResTC<C>::smem_floats * sizeof(float);
+    static bool attr_set[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        JK_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JK_CHECK_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+        attr_set[dev & 63] = true;
+    }
+    const long long per_clip = (T + ResTC<C>::TT - 1) / ResTC<C>::TT, total = per_clip * n;
+    const unsigned grid = (unsigned)std::min<long long>(total, sms[dev & 63]);
+    resblock_tc_kernel<C><<<grid, 256, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs, per_clip, total);
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // c_out <= 4 (the decoder's final Conv1d(emb_width -> 1 audio channel, k3), encdec.py:109): one thread per output
 // position, weights in shared memory.  The 64 x 64 tile kernel would spend 63/64 of its FMAs on padding here;
 // this one is a stream over the input (HBM bound).  Same accumulation order as the tile kernel (tap, then channel).
@@ -598,6 +758,16 @@ extern "C" int jk_resblock_cl(const float* x, float* out, float* tmp, const floa
     a.in = tmp; a.c_in = Cs; a.out = out; a.c_out = C; a.w = w2; a.bias = b2; a.res = x; a.n_taps = 1; a.tap_off[0] = 0;
     a.scale = res_scale;
     return jk_conv1d_cl(&a, stream);
+}
+
+extern "C" int jk_resblock_tc(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
+                              int n, int64_t T, int C, int dilation, float res_scale, jk_stream_t stream) {
+    JK_REQUIRE(x && out && w1 && w2 && b1 && b2, "null argument");
+    JK_REQUIRE(x != out && T > 0 && n > 0, "x and out must differ, T and n must be positive");
+    if (C == 64) return launch_resblock_tc<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    if (C == 32) return launch_resblock_tc<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    JK_REQUIRE(false, "jk_resblock_tc: C must be 32 or 64 (got %d)", C);
+    return 0;
 }
 
 extern "C" int jk_pack_conv_weight(const float* w, float* packed, int c_out, int c_in, int k, int transposed,

@@ -1,8 +1,10 @@
 """Encoder / Decoder conv stacks (reference: jukebox/vqvae/encdec.py), channels-last [N, T, C]."""
 import torch.nn as nn
 
+import os
+
 from .ops_cl import Conv1d, ConvTranspose1d
-from .resnet import Resnet1D
+from .resnet import Resnet1D, use_tensor_cores
 
 
 def assert_shape(x, exp_shape):
@@ -48,6 +50,10 @@ class DecoderConvBock(nn.Module):
                              checkpoint_res=checkpoint_res),
                     ConvTranspose1d(width, input_emb_width if i == (down_t - 1) else width, filter_t, stride_t, pad_t)))
         self.model = nn.Sequential(*blocks)
+        # decoder side: nothing downstream needs a fixed FMA order, so the residual blocks take the tensor-core kernel
+        # (JK_VQVAE_EXACT=1 keeps the exact-FMA kernel everywhere, e.g. to compare the two)
+        if not os.environ.get("JK_VQVAE_EXACT"):
+            use_tensor_cores(self)
 
     def forward(self, x):
         for m in self.model:

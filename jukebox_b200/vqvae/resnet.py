@@ -20,17 +20,24 @@ class ResConv1DBlock(nn.Module):
             nn.init.zeros_(self.model[-1].weight)
             nn.init.zeros_(self.model[-1].bias)
         self.res_scale = res_scale
+        # decoder-side stacks (Decoder, Conditioner) run this block on the tensor cores (3xTF32, jk_resblock_tc); the
+        # encoder feeds the bit-exact codebook argmin and keeps the exact-FMA kernel.  Set by `use_tensor_cores`.
+        self.tensor_cores = False
 
     def forward(self, x):
         c3, c1 = self.model[1], self.model[3]
         if c3.n_in == c3.n_out and c3.n_in in (32, 64):
-            # the VQ-VAE's own shapes: ONE launch, the hidden activation stays in shared memory (jk_resblock_cl)
+            # the VQ-VAE's own shapes: ONE launch, the hidden activation stays in shared memory
             x = x.contiguous()
             n, T, C_ = x.shape
             (w1, b1), (w2, b2) = c3.packed(), c1.packed()
             out = t.empty_like(x)
-            check(lib().jk_resblock_cl(ptr(x), ptr(out), None, ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, T, C_, c3.n_out,
-                                       c3.dilation, float(self.res_scale), stream_ptr()))
+            if self.tensor_cores:
+                check(lib().jk_resblock_tc(ptr(x), ptr(out), ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, T, C_, c3.dilation,
+                                           float(self.res_scale), stream_ptr()))
+            else:
+                check(lib().jk_resblock_cl(ptr(x), ptr(out), None, ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, T, C_, c3.n_out,
+                                           c3.dilation, float(self.res_scale), stream_ptr()))
             return out
         h = c3(x, relu_in=True)
         return c1(h, relu_in=True, res=x, scale=self.res_scale)
@@ -58,3 +65,11 @@ class Resnet1D(nn.Module):
         for blk in (self.blocks if self.checkpoint_res == 1 else self.model):
             x = blk(x)
         return x
+
+
+def use_tensor_cores(module, on=True):
+    """switch every ResConv1DBlock below `module` to the 3xTF32 tensor-core kernel (decoder-side stacks only)"""
+    for m in module.modules():
+        if isinstance(m, ResConv1DBlock):
+            m.tensor_cores = bool(on)
+    return module

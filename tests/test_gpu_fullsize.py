@@ -25,7 +25,8 @@ def prior_1b():
     import contextlib
     import bench
     with contextlib.redirect_stdout(sys.stderr):
-        p = bench.build_prior(False, seed=0)
+        p, hps = bench.build_prior(bench.WORKLOADS["1b_lyrics"], seed=0)
+        p._bench_hps = hps
     yield p
     del p
     torch.cuda.empty_cache()
@@ -75,7 +76,7 @@ def test_1b_lyrics_seeded_sampling_is_reproducible(prior_1b):
     import bench
     prior = prior_1b
     n = 4
-    y = bench.make_labels(prior, n, seed=7).cuda()
+    y = bench.make_labels(prior, prior._bench_hps, n, seed=7).cuda()
     outs = []
     for _ in range(2):
         torch.manual_seed(123)

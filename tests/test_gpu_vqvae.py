@@ -106,3 +106,28 @@ def test_decode_is_batch_independent_and_linear_in_out_bias():
         c = vq.decode([z[2:3] for z in zs[1:]], start_level=1)
     assert torch.equal(a, b)
     assert torch.equal(a[2:3], c)
+
+
+@pytest.mark.parametrize("C,dil,T", [(64, 1, 1000), (64, 2187, 5000), (32, 27, 777), (32, 1, 64), (64, 9, 65)])
+def test_tensor_core_resblock_matches_exact_fma_kernel(C, dil, T):
+    """jk_resblock_tc (3xTF32 on mma.sync, decoder side) against jk_resblock_cl (exact fp32 FMAs): same block
+    (resnet.py:27-44), fp32-level agreement; ragged T, dilations beyond the tile, both channel counts"""
+    import ctypes as Cc
+    from jukebox_b200._lib import lib, check, ptr, stream_ptr
+    g = torch.Generator(device="cuda").manual_seed(C + dil)
+    n = 2
+    x = torch.randn(n, T, C, device="cuda", generator=g)
+    w1 = torch.randn(3, C, C, device="cuda", generator=g) / (3 * C) ** 0.5
+    w2 = torch.randn(1, C, C, device="cuda", generator=g) / C ** 0.5
+    b1 = torch.randn(C, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(C, device="cuda", generator=g) * 0.1
+    exact, tc = torch.empty_like(x), torch.empty_like(x)
+    check(lib().jk_resblock_cl(ptr(x), ptr(exact), None, ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, T, C, C, dil, 0.7, stream_ptr()))
+    check(lib().jk_resblock_tc(ptr(x), ptr(tc), ptr(w1), ptr(b1), ptr(w2), ptr(b2), n, T, C, dil, 0.7, stream_ptr()))
+    ref = x.double() + 0.7 * (torch.einsum("ntc,cd->ntd", torch.relu(
+        sum(torch.einsum("ntc,cd->ntd", torch.relu(torch.nn.functional.pad(x.double(), (0, 0, dil, dil))[:, k * dil:k * dil + T]), w1[k].double())
+            for k in range(3)) + b1.double()), w2[0].double()) + b2.double())
+    e_exact = float((exact.double() - ref).abs().max() / ref.abs().max())
+    e_tc = float((tc.double() - ref).abs().max() / ref.abs().max())
+    print(f"C {C} dil {dil} T {T}: exact-FMA kernel vs fp64 {e_exact:.1e}, 3xTF32 kernel vs fp64 {e_tc:.1e}")
+    assert e_exact < 2e-6 and e_tc < 4e-6

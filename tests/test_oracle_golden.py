@@ -84,3 +84,23 @@ def test_philox_known_answers():
             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
     for ctr, key, out in kat:
         assert philox4x32_10(ctr, key) == out
+
+
+@pytest.mark.parametrize("tag", TR_CASES)
+def test_torch_restatement_is_the_reference_on_the_same_device(tag):
+    """oracle/transformer_torch.py (used on the GPU box to measure fp16 order noise) replays the reference's own
+    torch operators: on THIS box's CPU it must reproduce the reference's CPU outputs (bit for bit in fp16 up to the
+    rare GEMM-blocking difference, 2e-6 in fp32)"""
+    import torch
+    from oracle.transformer_torch import TorchDecodeOracle
+    fx = Fixture(f"transformer_{tag}")
+    c = fx.cfg
+    orc = TorchDecodeOracle(fx.weights(), c["n_in"], c["n_ctx"], c["n_head"], c["n_depth"], c["attn_order"], c["blocks"],
+                            c["encoder_dims"], c["prime_len"])
+    x = torch.from_numpy(fx["x"])
+    enc = torch.from_numpy(fx["encoder_kv"]) if "encoder_kv" in fx else None
+    for fp16, key, tol in ((True, "y16", 5e-4), (False, "y32", 2e-6)):
+        orc.reset()
+        with torch.no_grad():
+            y = torch.stack([orc.step(x[:, i], enc, fp16) for i in range(c["n_ctx"])], 1).numpy()
+        assert rel_err(y, fx[key]) < tol, (key, rel_err(y, fx[key]))

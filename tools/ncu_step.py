@@ -17,7 +17,7 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--pos", type=int, default=4000)
 args = ap.parse_args()
 with contextlib.redirect_stdout(sys.stderr):
-    prior = bench.build_prior(args.small)
+    prior, _ = bench.build_prior(bench.SMALL if args.small else bench.WORKLOADS['1b_lyrics'])
 ca = prior.prior
 n = 16
 eng = ca._engine(n)

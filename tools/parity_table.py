@@ -12,7 +12,8 @@ for line in open(src):
     rows[r["fixture"]] = r          # last run of a fixture wins
 out = ["Parity of the decode kernel at BASELINE geometry, measured on the B200 box (tests/test_gpu_fullsize_golden.py).",
        "Reference outputs: the UNMODIFIED reference run on CPU (oracle/make_golden_fullsize.py).  rel = max|a-b| / max|b|.",
-       "ref noise = the reference's fp16 path against itself with another prefill chunking / BLAS thread count (summation order only).",
+       "ref noise = the reference's own torch operators replayed on the B200 in fp16 (oracle/transformer_torch.py) against the",
+       "            reference's CPU fp16 output: the distance between two legitimate fp16 executions of the same path.",
        "",
        f"{'fixture':12s} {'ours vs ref fp16':>17s} {'ref fp16 noise':>15s} {'ours vs ref fp32':>17s} {'ref fp16 vs fp32':>17s} {'worst probe':>12s}"]
 for k in sorted(rows):
