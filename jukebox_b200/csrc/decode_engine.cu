@@ -56,7 +56,7 @@ constexpr int kHeaderBytes = 8192;     // barriers, LN statistics, descriptor / 
 constexpr int kLogitKT = 1024;         // K tile (floats) of the fp32 logits product
 constexpr int kLogitRowsPerChunk = 4;
 constexpr int kLogitRowsPerPass = 16;
-constexpr int kMaxSplit = 8;
+constexpr int kMaxSplit = 4;
 constexpr int kProfSlots = 1024;
 constexpr int kXpCols = 64;            // columns per unit in the partial-sum exchange (8 groups of 8)
 constexpr int kRedBytes = 8 * 16 * 72 * 4;   // cross-warp reduction tile [8 warps][16 rows][<= 72 floats]
@@ -85,6 +85,7 @@ struct StepArgs {
 //   [0, 192)      ring mbarriers          [256, 512)    LN row statistics + flags
 //   [512, 1024)   descriptor head         [1024, 1536)  two layer records (+ column assignment at +128)
 //   [2048, 6144)  residual-stream slice of this CTA: [16][32] float2
+//   [6144, 7704)  thread layouts of the activation staging (stage_map_init)
 extern __shared__ __align__(1024) uint8_t jk_smem[];
 __device__ __forceinline__ uint64_t* sm_full() { return reinterpret_cast<uint64_t*>(jk_smem); }
 __device__ __forceinline__ uint64_t* sm_empty() { return reinterpret_cast<uint64_t*>(jk_smem) + kMaxSlots; }
@@ -119,29 +120,43 @@ struct Ring {
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ int kpc_of(int ncg) {
-    int k = (64 / ncg) & ~7;
-    return k < 8 ? 8 : k;
-}
+// k-steps per ring slot for a unit of ncg column groups: the largest power of two with k * ncg * 256 B <= 16 KB
+__device__ __host__ __forceinline__ int kpc_of(int ncg) { return ncg == 1 ? 64 : ncg == 2 ? 32 : ncg <= 4 ? 16 : 8; }
 
 // ---- LL words ------------------------------------------------------------------------------
 // 8 bytes = {data (low 32 bits), flag (high 32 bits)}.  A naturally aligned 8-byte access is single-copy
 // atomic, so a reader that sees the flag sees the data; relaxed gpu-scope accesses go to L2 (no L1).
+#ifdef JK_WEAK_STORES       // A/B build only
+#define JK_ST_LL "st.global.cg"
+#else
+#define JK_ST_LL "st.relaxed.gpu.global"
+#endif
 __device__ __forceinline__ void ll_st(unsigned long long* p, uint32_t data, uint32_t flag) {
     const unsigned long long v = ((unsigned long long)flag << 32) | data;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile(JK_ST_LL ".u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Polled loads are WEAK loads that bypass L1 (ld.global.cg reads the L2 the producers' stores land in).  A strong
+// (ld.relaxed.gpu, SASS LDG.E.STRONG.GPU) load is not needed - nothing is inferred from one load about another, every
+// word carries its own flag - and strong loads do not pipeline: a thread's 8 - 16 polled loads cost one L2 round trip
+// EACH (measured with JK_NOWAIT: 1.1 us for 8 loads, 3 us for 32), weak ones overlap.
 __device__ __forceinline__ ulonglong2 ll_ld2(const unsigned long long* p) {
     ulonglong2 v;
+#ifdef JK_STRONG_LOADS      // A/B build only (tools/r2_job7.sh)
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+#else
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ unsigned long long ll_ld1(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ bool ll_ok(unsigned long long w, uint32_t flag) { return (uint32_t)(w >> 32) == flag; }
+// tuning aid (JK_NOWAIT=1): hand-overs stop waiting (results are garbage) - what remains is every CTA's own work, so
+// step time with and without it separates "waiting for other SMs" from "work on the critical path of one SM"
+__constant__ int jk_nowait;
+__device__ __forceinline__ bool ll_ok(unsigned long long w, uint32_t flag) { return ((uint32_t)(w >> 32) == flag) | (jk_nowait != 0); }
 __device__ __forceinline__ void spin_guard(unsigned& spins) {
     if (++spins > (1u << 24)) __trap();     // a protocol bug traps instead of hanging the GPU
 }
@@ -156,7 +171,7 @@ __device__ __forceinline__ uint32_t ll_wait1(const unsigned long long* p, uint32
 __device__ __forceinline__ unsigned long long wait_stat_word(const long long* p, int G) {
     unsigned spins = 0;
     unsigned long long w = ll_ld1(reinterpret_cast<const unsigned long long*>(p));
-    while ((int)(w >> kCntShift) != G) { spin_guard(spins); w = ll_ld1(reinterpret_cast<const unsigned long long*>(p)); }
+    while ((int)(w >> kCntShift) != G && !jk_nowait) { spin_guard(spins); w = ll_ld1(reinterpret_cast<const unsigned long long*>(p)); }
     return w;
 }
 
@@ -190,8 +205,8 @@ __device__ __forceinline__ void red_add_u64(long long* p, unsigned long long v) 
 }
 __device__ __forceinline__ long long* sm_sfx() { return reinterpret_cast<long long*>(sm_uni() + kRedBytes); }
 
-// This CTA's contribution to the statistics block `ln_out` ([16 rows][2 moments], one 128-byte line each).
-// sfx: [2][1024] fixed-point values of the elements it wrote, element e belongs to row e / ppc.  32 threads each
+// This CTA's contribution to the statistics block `ln_out` ([16 rows] x {sum, sumsq} adjacent, one 128-byte line per row).
+// sfx: [2][16 rows][32] fixed-point values of the column pairs it wrote.  32 threads each
 // reduce one (row, moment) in a fixed order and issue ONE 64-bit red carrying value + count.
 __device__ __forceinline__ void publish_stats(long long* ln_out, int B, int ppc) {
     const int tid = threadIdx.x;
@@ -200,8 +215,8 @@ __device__ __forceinline__ void publish_stats(long long* ln_out, int B, int ppc)
         const long long* sfx = sm_sfx() + (tid & 1) * 1024;
         const int row = tid >> 1;
         long long s = (tid & 1) ? 0 : kSumBias;
-        for (int i = 0; i < ppc; ++i) s += sfx[row * ppc + i];
-        red_add_u64(ln_out + 16 * tid, (1ull << kCntShift) + (unsigned long long)s);
+        for (int i = 0; i < ppc; ++i) s += sfx[row * 32 + i];
+        red_add_u64(ln_out + 16 * row + (tid & 1), (1ull << kCntShift) + (unsigned long long)s);
     }
     consumer_sync();                       // the scratch is reused by the next phase
 }
@@ -211,42 +226,54 @@ __device__ __forceinline__ void publish_stats(long long* ln_out, int B, int ppc)
 // Threads are laid out [row group][8-column vector]: a thread keeps ONE column vector (gamma / beta loaded
 // once) and walks rows rg, rg + rgc, ...; four rows = eight 16-byte polled loads in flight per batch.
 // Rows >= B are never written: an MMA output row depends only on its own A row, and those outputs are discarded.
+// How the 256 consumer threads tile a [16 rows][Ks / 8 vectors] slice: cw column vectors per pass x rgc row groups,
+// thread -> (column vector cv, row group rg).  Computed once per launch for the three K of a layer (kind 0: width,
+// 1: n_state, 2: mlp width) and kept in the shared-memory header: [6144 + 512 * kind + 2 * tid] = cv | rg << 8,
+// [7680 + 8 * kind] = {cw, rgc} - so no integer division sits on the path of a phase.
+__device__ __forceinline__ void stage_map_init(int kind, int Ks) {
+    const int nvec = Ks >> 3, tid = threadIdx.x;
+    const int cw = nvec >= kConsumers ? kConsumers : nvec;
+    const int rgc = nvec >= kConsumers ? 1 : kConsumers / nvec;
+    reinterpret_cast<unsigned short*>(jk_smem + 6144 + 512 * kind)[tid] = (unsigned short)((tid % cw) | ((tid / cw) << 8));
+    if (tid == 0) {
+        reinterpret_cast<int*>(jk_smem + 7680 + 8 * kind)[0] = cw;
+        reinterpret_cast<int*>(jk_smem + 7680 + 8 * kind)[1] = rgc;
+    }
+}
+
 __device__ __noinline__ void stage_acts(const unsigned long long* in, int K, int k0, int Ks, int B, uint32_t flag, int ln,
-                                        const float* gamma, const float* beta, const long long* lnacc) {
+                                        const float* gamma, const float* beta, const long long* lnacc, int kind) {
     const int tid = threadIdx.x;
     uint8_t* acts = sm_uni();
     float* stats = sm_stats();
     const int nvec = Ks >> 3;
     const int astride = (Ks + 8) * 2;
-    if (ln && tid < 32) {
-        // lanes 2r / 2r+1 poll the sum / sum-of-squares word of row r until every CTA has contributed
+    if (ln && tid < 16) {
+        // lane r polls the two adjacent words (sum, sum of squares) of row r with one 16-byte load until every CTA has
+        // contributed to both: 16 pollers per CTA on 16 lines
         const int G = sm_E()->G;
-        long long val = 0;
-        if (tid < 2 * B) {
-            const unsigned long long w = wait_stat_word(lnacc + 16 * tid, G);
-            val = (long long)(w & kValMask) - ((tid & 1) ? 0ll : (long long)G * kSumBias);
+        float mean = 0.f, rstd = 0.f;
+        if (tid < B) {
+            const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(lnacc + 16 * tid);
+            unsigned spins = 0;
+            ulonglong2 w = ll_ld2(wp);
+            while (((int)(w.x >> kCntShift) != G || (int)(w.y >> kCntShift) != G) && !jk_nowait) { spin_guard(spins); w = ll_ld2(wp); }
+            const long long val = (long long)(w.x & kValMask) - (long long)G * kSumBias, sq = (long long)(w.y & kValMask);
+            // double only for the cancellation in E[x^2] - mean^2 (adds / muls; no double div or sqrt:
+            // those are kilobytes of library code in the instruction cache)
+            const double rk = (double)(1.0f / (float)K);    // K is a multiple of 16: exact for powers of two, 1e-7 rel otherwise
+            const double m = (double)val * (1.0 / 65536.0) * rk;
+            double var = (double)sq * (1.0 / 16384.0) * rk - m * m;
+            var = var < 0.0 ? 0.0 : var;
+            rstd = 1.0f / sqrtf((float)var + 1e-5f);
+            mean = -(float)m * rstd;                        // staged as x * rstd + (-mean * rstd), then * gamma + beta
         }
-        const long long sq = __shfl_xor_sync(0xffffffffu, val, 1);
-        if (!(tid & 1)) {
-            const int row = tid >> 1;
-            float mean = 0.f, rstd = 0.f;
-            if (row < B) {
-                // double only for the cancellation in E[x^2] - mean^2 (adds / muls; no double div or sqrt:
-                // those are kilobytes of library code in the instruction cache)
-                const double rk = (double)(1.0f / (float)K);    // K is a multiple of 16: exact for powers of two, 1e-7 rel otherwise
-                const double m = (double)val * (1.0 / 65536.0) * rk;
-                double var = (double)sq * (1.0 / 16384.0) * rk - m * m;
-                var = var < 0.0 ? 0.0 : var;
-                rstd = 1.0f / sqrtf((float)var + 1e-5f);
-                mean = -(float)m * rstd;                        // staged as x * rstd + (-mean * rstd), then * gamma + beta
-            }
-            stats[2 * row] = mean;
-            stats[2 * row + 1] = rstd;
-        }
+        stats[2 * tid] = mean;
+        stats[2 * tid + 1] = rstd;
     }
-    const int cw = nvec >= kConsumers ? kConsumers : nvec;           // column vectors covered per pass
-    const int rgc = nvec >= kConsumers ? 1 : kConsumers / nvec;      // row groups
-    const int cv = tid % cw, rg = tid / cw;
+    const int cw = reinterpret_cast<const int*>(jk_smem + 7680 + 8 * kind)[0], rgc = reinterpret_cast<const int*>(jk_smem + 7680 + 8 * kind)[1];
+    const unsigned tm = reinterpret_cast<const unsigned short*>(jk_smem + 6144 + 512 * kind)[tid];
+    const int cv = tm & 255, rg = tm >> 8;
     const int row_words = K >> 1;
     bool stats_ready = !ln;
 #pragma unroll 1
@@ -358,15 +385,16 @@ struct GemmArgs {
     const float *gamma, *beta, *bias;
     const long long* ln_in;             // statistics block behind the input (LayerNorm phases)
     long long* ln_out;                  // statistics block of the rows this epilogue writes (residual epilogues)
+    int kind;                           // 0: K = width, 1: K = n_state, 2: K = mlp width (thread layout of the staging)
 };
 
 __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
     const EngineDev* E = sm_E();
     uint8_t* uni = sm_uni();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KS = E->KS, c = blockIdx.x, rank = c % KS;
+    const int KS = E->KS, ksh = E->ks_shift, c = blockIdx.x, rank = c & (KS - 1);
     const int ncg = g.ncg, nc = ncg * 8;
-    const int ppc = (nc >> 1) / KS;                      // column pairs this CTA finishes
+    const int ppc = (nc >> 1) >> ksh;                    // column pairs this CTA finishes
     const bool residual = (g.epi == EPI_PROJ || g.epi == EPI_PROJ2);
     STAMP(E, g.pslot, 0);
     if (ncg == 0) {                                      // a unit without columns (tiny models) still contributes (count only)
@@ -374,8 +402,8 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
         return ring;
     }
     const int K = g.K, N = g.N, epi = g.epi;
-    const int Ks = K / KS, k0 = rank * Ks;
-    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in);
+    const int Ks = K >> ksh, k0 = rank * Ks;
+    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in, g.kind);
     consumer_sync();
     STAMP(E, g.pslot, 1);
 
@@ -383,9 +411,53 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
     const int nkk = Ks >> 4;
-    const int kpc = kpc_of(ncg);
+    const int kpc = kpc_of(ncg);                          // a power of two
     const int astride = (Ks + 8) * 2;
     const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
+    const int xp_direct = E->xp_direct;
+    const bool colpar = (KS > 1 && xp_direct == 2);
+    if (colpar) {
+        // ---- column-parallel: warp j multiplies ALL k-steps of the CTA's K slice for column group j.  Its sums are
+        // complete over the slice, so there is no cross-warp reduction: the warp publishes its [16 x 8] tile straight
+        // from registers.  Two accumulators (even / odd k-steps) halve the HMMA dependency chain.
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool mine = warp < ncg;
+#pragma unroll 1
+        for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {
+            mbar_wait(ring.full(), ring.phase);
+            if (mine) {
+                const int nk = min(kpc, nkk - kk0);
+                const uint32_t sl = smem_u32(ring.data()) + lane * 8 + (warp << 8);
+#pragma unroll 4
+                for (int i = 0; i < nk; i += 2) {
+                    uint32_t a0[4], a1[4];
+                    ldsm4(a0, arow + (kk0 + i) * 32);
+                    const uint2 b0 = lds64(sl + ((i * ncg) << 8));
+                    mma_16816(c0, a0, b0.x, b0.y);
+                    if (i + 1 < nk) {
+                        ldsm4(a1, arow + (kk0 + i + 1) * 32);
+                        const uint2 b1 = lds64(sl + (((i + 1) * ncg) << 8));
+                        mma_16816(c1, a1, b1.x, b1.y);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ring.empty());
+            ring.advance();
+        }
+        if (mine) {
+            const int r0 = lane >> 2, pq = lane & 3;
+            unsigned long long* base = g.xp + ((size_t)c * 8 * 16) * kXpCols;          // slot 0 of this rank
+            const unsigned long long fl = (unsigned long long)g.flag_in << 32;
+            unsigned long long* d0 = base + (size_t)r0 * kXpCols + 2 * (warp * 4 + pq);
+            if (r0 < B)
+                asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(d0), "l"(fl | __float_as_uint(c0[0] + c1[0])),
+                             "l"(fl | __float_as_uint(c0[1] + c1[1])) : "memory");
+            if (r0 + 8 < B)
+                asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(d0 + 8 * kXpCols), "l"(fl | __float_as_uint(c0[2] + c1[2])),
+                             "l"(fl | __float_as_uint(c0[3] + c1[3])) : "memory");
+        }
+    } else {
     // slot s of this Conv1D is multiplied by warp s % 8 alone.  EVERY warp still waits for the slot and arrives on its
     // empty barrier: the parity protocol of the ring only holds while no warp is a whole ring ahead of or behind the
     // producer (a warp that skipped the handshake of foreign slots aliased phases once a Conv1D had more slots than
@@ -416,94 +488,136 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
         default: JK_MMA_LOOP(8) break;
     }
 #undef JK_MMA_LOOP
+    }
     STAMP(E, g.pslot, 2);
-    consumer_sync();                       // everyone is done reading the staged activations
-    // cross-warp reduction tile [warps that owned a slot][16 rows][ncp floats]; ncp = 8 mod 32 keeps both the fragment
-    // stores below and the row-wise pair loads of the epilogue free of bank conflicts
+    const int nwarp = min(8, (nkk + kpc - 1) >> (31 - __clz(kpc)));       // warps that multiplied at least one slot
     float* red = reinterpret_cast<float*>(uni);
     const int ncp = ((nc + 31) & ~31) + 8;
-    const int nwarp = min(8, (nkk + kpc - 1) / kpc);
-    if (warp < nwarp) {
-        const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+    // partial sums of the unit: [KS ranks][8 warps][16 rows][64 columns] LL words {fp32, flag}
+    unsigned long long* xp_unit = g.xp + (size_t)(c - rank) * 8 * 16 * kXpCols;
+    if (colpar) {
+        // partial tiles are already in the exchange buffer
+    } else if (KS > 1 && xp_direct) {
+        // ---- the partial sums of the unit meet in the exchange buffer: every warp that multiplied publishes its
+        // accumulator fragments straight from registers (no shared-memory reduction, no CTA barrier on this path)
+        if (warp < nwarp) {
+            const int r0 = lane >> 2, pq = lane & 3;
+            unsigned long long* base = xp_unit + (size_t)(rank * 8 + warp) * 16 * kXpCols;
+            const unsigned long long fl = (unsigned long long)g.flag_in << 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < ncg) {
-                float* d = red + (size_t)(warp * 16) * ncp + j * 8 + c0;
-                *reinterpret_cast<float2*>(d + r0 * ncp) = make_float2(acc[j][0], acc[j][1]);
-                *reinterpret_cast<float2*>(d + (r0 + 8) * ncp) = make_float2(acc[j][2], acc[j][3]);
+            for (int j = 0; j < 8; ++j) {
+                if (j < ncg) {
+                    unsigned long long* d0 = base + (size_t)r0 * kXpCols + 2 * (j * 4 + pq);
+                    if (r0 < B)
+                        asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(d0), "l"(fl | __float_as_uint(acc[j][0])),
+                                     "l"(fl | __float_as_uint(acc[j][1])) : "memory");
+                    if (r0 + 8 < B)
+                        asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(d0 + 8 * kXpCols), "l"(fl | __float_as_uint(acc[j][2])),
+                                     "l"(fl | __float_as_uint(acc[j][3])) : "memory");
+                }
             }
         }
-    }
-    consumer_sync();
-    // ---- the KS partial sums of the unit meet: everyone publishes all of its columns ... -------------------
-    const int npair = nc >> 1;
-    unsigned long long* xp_unit = g.xp + (size_t)(c - rank) * 16 * kXpCols;      // [KS][16][64]
-    if (KS > 1) {
+    } else {
+        consumer_sync();                   // everyone is done reading the staged activations
+        // cross-warp reduction tile [warps that owned a slot][16 rows][ncp floats]; ncp = 8 mod 32 keeps both the fragment
+        // stores below and the row-wise pair loads of the epilogue free of bank conflicts
+        if (warp < nwarp) {
+            const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < ncg) {
+                    float* d = red + (size_t)(warp * 16) * ncp + j * 8 + c0;
+                    *reinterpret_cast<float2*>(d + r0 * ncp) = make_float2(acc[j][0], acc[j][1]);
+                    *reinterpret_cast<float2*>(d + (r0 + 8) * ncp) = make_float2(acc[j][2], acc[j][3]);
+                }
+            }
+        }
+        consumer_sync();
+        if (KS > 1 && lane < (nc >> 1)) {
+            // one partial per rank: the warps' tiles summed here, published in slot 0 of this rank (lane = column pair,
+            // warp = sample row and row + 8)
 #pragma unroll 1
-        for (int e = tid; e < B * npair; e += kConsumers) {
-            const int b = e / npair, pr = e - b * npair;
-            float s0 = 0.f, s1 = 0.f;
-            for (int w = 0; w < nwarp; ++w) {
-                const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
-                s0 += v.x; s1 += v.y;
+            for (int b = warp; b < B; b += 8) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int w = 0; w < nwarp; ++w) {
+                    const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * lane);
+                    s0 += v.x; s1 += v.y;
+                }
+                unsigned long long* dst = xp_unit + ((size_t)(rank * 8) * 16 + b) * kXpCols + 2 * lane;
+                const unsigned long long fl = (unsigned long long)g.flag_in << 32;
+                asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(fl | __float_as_uint(s0)),
+                             "l"(fl | __float_as_uint(s1)) : "memory");
             }
-            unsigned long long* dst = xp_unit + ((size_t)rank * 16 + b) * kXpCols + 2 * pr;
-            const unsigned long long w0 = ((unsigned long long)g.flag_in << 32) | __float_as_uint(s0);
-            const unsigned long long w1 = ((unsigned long long)g.flag_in << 32) | __float_as_uint(s1);
-            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
         }
     }
+    const int nw_xp = (xp_direct == 1) ? nwarp : 1;              // partial words per rank in the exchange buffer
+    if (KS > 1 && xp_direct && 16 * astride > kRedBytes) consumer_sync();     // the statistics scratch below would overlap a still-read A tile
     STAMP(E, g.pslot, 3);
     // ---- ... and finishes its own column pairs ----------------------------------------------------------
     float2* res = sm_res();
-    long long* sfx = sm_sfx();                                        // [2][1024] statistics of the elements written
-    const int n_el = B * ppc;
-#pragma unroll 1
-    for (int e = tid; e < n_el; e += kConsumers) {
-        const int b = e / ppc, pl = e - b * ppc;
+    long long* sfx = sm_sfx();                                        // [2][16][32] statistics of the pairs written
+    if (lane < ppc) {
+        const int pl = lane;
         const int pr = rank * ppc + pl;                 // pair inside the unit
         const int gc = g.g0 * 8 + 2 * pr;               // global column of the pair
         const float2 bias = *reinterpret_cast<const float2*>(g.bias + gc);
-        float s0 = 0.f, s1 = 0.f;
-        if (KS == 1) {
-            for (int w = 0; w < nwarp; ++w) {
-                const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
-                s0 += v.x; s1 += v.y;
+#pragma unroll 1
+        for (int b = warp; b < B; b += 8) {                 // this thread's rows: warp and warp + 8
+            float s0 = 0.f, s1 = 0.f;
+            if (KS == 1) {
+                for (int w = 0; w < nwarp; ++w) {
+                    const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
+                    s0 += v.x; s1 += v.y;
+                }
+            } else {
+                // KS x nwarp partial words per pair and row, polled KS x 4 at a time and summed in (warp, rank) order:
+                // a fixed order, so the result is bit-reproducible
+#pragma unroll 1
+                for (int w0 = 0; w0 < nw_xp; w0 += 4) {
+                    ulonglong2 v[4][4];
+                    unsigned spins = 0;
+                    bool again;
+                    do {
+                        again = false;
+#pragma unroll
+                        for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q < KS && w0 + wi < nw_xp)
+                                    v[wi][q] = ll_ld2(xp_unit + ((size_t)(q * 8 + w0 + wi) * 16 + b) * kXpCols + 2 * pr);
+#pragma unroll
+                        for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q < KS && w0 + wi < nw_xp) again |= !(ll_ok(v[wi][q].x, g.flag_in) && ll_ok(v[wi][q].y, g.flag_in));
+                        if (again) spin_guard(spins);
+                    } while (again);
+#pragma unroll
+                    for (int wi = 0; wi < 4; ++wi)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < KS && w0 + wi < nw_xp) {
+                                s0 += __uint_as_float((uint32_t)v[wi][q].x); s1 += __uint_as_float((uint32_t)v[wi][q].y);
+                            }
+                }
             }
-        } else {
-            ulonglong2 v[4];
-            unsigned spins = 0;
-            bool again;
-            do {
-                again = false;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < KS) v[q] = ll_ld2(xp_unit + ((size_t)q * 16 + b) * kXpCols + 2 * pr);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < KS) again |= !(ll_ok(v[q].x, g.flag_in) && ll_ok(v[q].y, g.flag_in));
-                if (again) spin_guard(spins);
-            } while (again);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q < KS) { s0 += __uint_as_float((uint32_t)v[q].x); s1 += __uint_as_float((uint32_t)v[q].y); }
+            const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
+            __half2 o;
+            if (epi == EPI_QKV) {
+                o = __floats2half2_rn(y0, y1);
+            } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
+                o = __floats2half2_rn(quick_gelu_f(y0), quick_gelu_f(y1));
+            } else {
+                // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
+                const float2 base = res[b * 32 + pl];
+                const float o0 = h2f_round(base.x + y0), o1 = h2f_round(base.y + y1);
+                res[b * 32 + pl] = make_float2(o0, o1);
+                o = __floats2half2_rn(o0, o1);
+                sfx[b * 32 + pl] = fx_sum(o0) + fx_sum(o1);
+                sfx[1024 + b * 32 + pl] = fx_sq(o0) + fx_sq(o1);
+            }
+            ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
         }
-        const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
-        __half2 o;
-        if (epi == EPI_QKV) {
-            o = __floats2half2_rn(y0, y1);
-        } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
-            o = __floats2half2_rn(quick_gelu_f(y0), quick_gelu_f(y1));
-        } else {
-            // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
-            const float2 base = res[b * 32 + pl];
-            const float o0 = h2f_round(base.x + y0), o1 = h2f_round(base.y + y1);
-            res[b * 32 + pl] = make_float2(o0, o1);
-            o = __floats2half2_rn(o0, o1);
-            sfx[e] = fx_sum(o0) + fx_sum(o1);
-            sfx[1024 + e] = fx_sq(o0) + fx_sq(o1);
-        }
-        ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
     }
     STAMP(E, g.pslot, 4);
     if (residual) publish_stats(g.ln_out, B, ppc);
@@ -522,16 +636,17 @@ struct AttnGeom {
     int wrow;     // cache row the current token's k/v is written to (-1: none)
 };
 
-__device__ __forceinline__ AttnGeom attn_geom(const EngineDev* E, const LayerDev& LD, int p) {
+// pm = p % block_ctx, pd = p / block_ctx: computed once per launch
+__device__ __forceinline__ AttnGeom attn_geom(const EngineDev* E, const LayerDev& LD, int p, int pm, int pd) {
     AttnGeom g;
     const int bc = E->bc;
     switch (LD.attn_func) {
         case 0: g.R = p + 1; g.base = 0; g.cur = 1; g.wrow = p; break;
-        case 1: g.R = p % bc + 1; g.base = 0; g.cur = 1; g.wrow = p % bc; break;
-        case 2: g.base = (p % bc) * E->blocks; g.R = p / bc + 1; g.cur = 1; g.wrow = g.base + p / bc; break;
+        case 1: g.R = pm + 1; g.base = 0; g.cur = 1; g.wrow = pm; break;
+        case 2: g.base = pm * E->blocks; g.R = pd + 1; g.cur = 1; g.wrow = g.base + pd; break;
         case 3:
-            g.R = (p >= bc) ? bc : 0; g.base = ((p / bc + 1) & 1) * bc; g.cur = 0;
-            g.wrow = ((p / bc) & 1) * bc + p % bc; break;
+            g.R = (p >= bc) ? bc : 0; g.base = ((pd + 1) & 1) * bc; g.cur = 0;
+            g.wrow = (pd & 1) * bc + pm; break;
         case 7:
             g.R = min(p + 1, E->prime_pad); g.base = 0; g.cur = (p < E->prime_pad) ? 1 : 0;
             g.wrow = (p < E->prime_pad) ? p : -1; break;
@@ -548,11 +663,15 @@ __device__ __host__ __forceinline__ int attn_tile_rows(int dhp) {
 
 // how many CTAs share one (sample, head): as few as keep every part inside ONE shared-memory tile
 // (RC - 1 cached rows + the current token's row), bounded by the grid
-__device__ __forceinline__ int attn_nsplit(const EngineDev* E, int B, int ncache) {
+// (gmax = G / (B * H) is computed once per launch; no division here)
+__device__ __forceinline__ int attn_nsplit(const EngineDev* E, int gmax, int ncache) {
     const int cap = E->RC - 1;
-    int ns = (ncache + cap - 1) / cap;
-    ns = min(ns, E->G / (B * E->H));
-    return max(1, min(kMaxSplit, ns));
+    const int ns = 1 + (ncache > cap) + (ncache > 2 * cap) + (ncache > 3 * cap);        // <= kMaxSplit
+    return max(1, min(ns, gmax));
+}
+// x / d for d in 1..4 and 0 <= x < 98304
+__device__ __forceinline__ int div_small(int x, int d) {
+    return d == 1 ? x : d == 2 ? (x >> 1) : d == 4 ? (x >> 2) : (int)(((unsigned)x * 43691u) >> 17);
 }
 
 __device__ __forceinline__ void ldsm4_trans(uint32_t (&r)[4], uint32_t addr) {
@@ -635,7 +754,7 @@ __device__ __noinline__ void attn_merge(int item, int ns, int b, int h, uint32_t
     const float* p0 = E->part + ((size_t)(item * kMaxSplit)) * (dhp + 2);
     const int st = dhp + 2;
     const int d = 2 * tid;                  // dims d, d+1 (dh is even, dh <= 512)
-    if (ns <= 4) {
+    {
         // every load of the merge is issued before the first use: ONE L2 round trip instead of three
         // dependent ones (max pass, sum pass, value pass) on the critical path of the slowest CTAs
         float m[4], l[4];
@@ -659,20 +778,6 @@ __device__ __noinline__ void attn_merge(int item, int ns, int b, int h, uint32_t
             }
         }
         if (d < dh) attn_out_pair(E, b, h, d, o0 / Lsum, o1 / Lsum, flag);
-    } else {
-        float M = -INFINITY;
-        for (int q = 0; q < ns; ++q) M = fmaxf(M, __ldcg(p0 + (size_t)q * st));
-        float Lsum = 0.f;
-        for (int q = 0; q < ns; ++q) Lsum += __ldcg(p0 + (size_t)q * st + 1) * expf(__ldcg(p0 + (size_t)q * st) - M);
-        if (d < dh) {
-            float o0 = 0.f, o1 = 0.f;
-            for (int q = 0; q < ns; ++q) {
-                const float w = expf(__ldcg(p0 + (size_t)q * st) - M);
-                const float2 v = __ldcg(reinterpret_cast<const float2*>(p0 + (size_t)q * st + 2 + d));
-                o0 += v.x * w; o1 += v.y * w;
-            }
-            attn_out_pair(E, b, h, d, o0 / Lsum, o1 / Lsum, flag);
-        }
     }
 }
 
@@ -714,7 +819,7 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     const bool last_part = (s == ns - 1);
     const int R = G.R;
     const int ncache = R - ((R > 0 && G.cur) ? 1 : 0);               // rows that come from the cache
-    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
+    const int i0 = div_small(ncache * s, ns), i1 = div_small(ncache * (s + 1), ns);
     const __half* kbase = LD.kc + (cbase + G.base) * dhp;
     const __half* vbase = LD.vc + (cbase + G.base) * dhp;
     const int trows = RC - 1;
@@ -870,19 +975,19 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
 // The cached K/V rows of this CTA's first attention item do not depend on the current token: issue their cp.async BEFORE
 // the layer's QKV Conv1D, into the tile region that only the attention phase uses, so that the HBM latency hides behind
 // that phase.  Returns 1 if the tile is on its way.
-__device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t) {
+__device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, int t, int pm, int pd, int gmax) {
     const EngineDev* E = sm_E();
     if (!E->kv_prefetch) return 0;
     const LayerDev LD = LD_ref;
-    const AttnGeom G = attn_geom(E, LD, t);
+    const AttnGeom G = attn_geom(E, LD, t, pm, pd);
     if (G.R == 0) return 0;
     const int ncache = G.R - (G.cur ? 1 : 0);
-    const int ns = attn_nsplit(E, B, ncache);
+    const int ns = attn_nsplit(E, gmax, ncache);
     if (c >= B * E->H * ns) return 0;
-    const int s = c % ns, bh = c / ns, b = bh / E->H, h = bh % E->H;
+    const int bh = div_small(c, ns), s = c - bh * ns, b = bh / E->H, h = bh - b * E->H;
     const int dhp = E->dh_pad, nvec = dhp >> 3, RC = E->RC;
     const int swz = (nvec & 7) ? 0 : 7;
-    const int i0 = (int)(((long long)ncache * s) / ns), i1 = (int)(((long long)ncache * (s + 1)) / ns);
+    const int i0 = div_small(ncache * s, ns), i1 = div_small(ncache * (s + 1), ns);
     const int nr = max(0, min(RC - 1, i1 - i0));
     const size_t cbase = ((size_t)(b * E->H + h)) * LD.rows;
     const uint32_t kd = smem_u32(jk_smem + kHeaderBytes + E->uni_bytes), vd = kd + RC * dhp * 2;
@@ -896,10 +1001,10 @@ __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, 
 __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int c) {
     if ((threadIdx.x & 31) != 0) return;
     const uint8_t* src = E->streams + (size_t)c * E->stream_stride;
-    const int KS = E->KS, u = c / KS;
+    const int KS = E->KS, u = c >> E->ks_shift;
     for (int l = 0; l < E->depth; ++l) {
         const ushort2* cl = E->cols + ((size_t)u * E->depth + l) * 4;
-        const int Ks[4] = {E->W / KS, E->S / KS, E->W / KS, E->M / KS};
+        const int Ks[4] = {E->W >> E->ks_shift, E->S >> E->ks_shift, E->W >> E->ks_shift, E->M >> E->ks_shift};
         if (c == (l % E->G)) {
             // biases + LayerNorm parameters of this layer (one contiguous block, ~57 KB for 1b_lyrics) are
             // shared by every CTA and evicted from L2 between steps: pull them into L2 ahead of the consumers
@@ -1013,7 +1118,8 @@ __device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref,
                     const int nr = min(kLogitRowsPerChunk, pe - r);
                     mbar_wait(ring.full(), ring.phase);
                     const float* wsl = reinterpret_cast<const float*>(ring.data());
-                    for (int k = lane * 4; k < kt; k += 128) {
+#pragma unroll 1
+                    for (int k = lane * 4; k < kt; k += 128) {      // rolled: this phase runs once per step, its code must stay small
                         float4 a0 = *reinterpret_cast<const float4*>(y0 + k);
                         float4 a1 = *reinterpret_cast<const float4*>(y1 + k);
 #pragma unroll
@@ -1056,7 +1162,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         reinterpret_cast<uint32_t*>(jk_smem + 1024)[tid] = reinterpret_cast<const uint32_t*>(&Eg->layer[0])[tid];
     __syncthreads();
     const EngineDev* E = sm_E();
-    const int KS = E->KS, unit = c / KS, rank = c % KS;
+    const int KS = E->KS, unit = c >> E->ks_shift, rank = c & (KS - 1);
     if (tid >= 32 && tid < 36)
         reinterpret_cast<uint32_t*>(jk_smem + 1024 + 128)[tid - 32] =
             reinterpret_cast<const uint32_t*>(E->cols + ((size_t)unit * E->depth + 0) * 4)[tid - 32];
@@ -1092,9 +1198,25 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         if (c == 0 && tid < 32) {                                                              \
             if (tid == 0) wait_stat_word(LN_BLOCK(seen_), G);                                  \
             __syncwarp();                                                                      \
-            LN_BLOCK(clear_)[16 * tid] = 0;                                                    \
+            LN_BLOCK(clear_)[16 * (tid >> 1) + (tid & 1)] = 0;                                 \
         }                                                                                      \
     } while (0)
+    // thread layouts of the activation staging for the three K of a layer (integer divisions: once per launch, not per phase)
+    // per-launch constants that need an integer division live in shared memory (not in registers across the phase calls):
+    // [7712] p % block_ctx, [7716] p / block_ctx, [7720] CTAs available per (sample, head)
+    if (tid == 0) {
+        int* gq = reinterpret_cast<int*>(jk_smem + 7712);
+        gq[0] = E->blocks > 0 ? t % E->bc : 0;
+        gq[1] = E->blocks > 0 ? t / E->bc : 0;
+        gq[2] = max(1, G / (B * E->H));
+    }
+#define PM (reinterpret_cast<const int*>(jk_smem + 7712)[0])
+#define PD (reinterpret_cast<const int*>(jk_smem + 7712)[1])
+#define GMAX (reinterpret_cast<const int*>(jk_smem + 7712)[2])
+    stage_map_init(0, W >> E->ks_shift);
+    stage_map_init(1, S >> E->ks_shift);
+    stage_map_init(2, M >> E->ks_shift);
+    consumer_sync();
     unsigned nph = 0;                                             // phase index (profiling slots)
 #define PHASE_DONE()                                                                           \
     do {                                                                                       \
@@ -1123,11 +1245,12 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     // This CTA embeds exactly the columns of the residual stream it will own for the whole stack.
     {
         const ushort2 wc = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 128)[1];     // column groups of width-W outputs
-        const int ppc = (wc.y * 4) / KS, n_el = B * ppc;
+        const int ppc = (wc.y * 4) >> E->ks_shift;
         float2* res = sm_res();
         long long* sfx = sm_sfx();
-        for (int e = tid; e < n_el; e += kConsumers) {
-            const int b = e / ppc, pl = e - b * ppc;
+        const int lane = tid & 31;
+        for (int b = warp; b < B && lane < ppc; b += 8) {     // lane = column pair, warp = sample row (and row + 8)
+            const int pl = lane;
             const int col = wc.x * 8 + 2 * (rank * ppc + pl);
             float2 x;
             if (A.x_in) {
@@ -1146,8 +1269,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             const __half2 hh = __floats2half2_rn(x.x, x.y);
             const float2 hv = __half22float2(hh);
             res[b * 32 + pl] = hv;
-            sfx[e] = fx_sum(hv.x) + fx_sum(hv.y);
-            sfx[1024 + e] = fx_sq(hv.x) + fx_sq(hv.y);
+            sfx[b * 32 + pl] = fx_sum(hv.x) + fx_sum(hv.y);
+            sfx[1024 + b * 32 + pl] = fx_sq(hv.x) + fx_sq(hv.y);
             ll_st(E->ll_h + (((size_t)b * W + col) >> 1), *reinterpret_cast<const uint32_t*>(&hh), fbase + 1);
         }
         publish_stats(LN_BLOCK(0), B, ppc);
@@ -1160,7 +1283,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
         const int Nqkv = (LD.attn_func == 6) ? S : 3 * S;
         const uint32_t fl = fbase + (uint32_t)l + 1;              // flag of this layer's buffers
-        const int pre = attn_prefetch(LD, B, c, t);
+        const int pre = attn_prefetch(LD, B, c, t, PM, PD, GMAX);
         // a fresh argument record per phase: nothing of it stays live across the calls in between
         if (l == 1) PROF3(0, 0);
         {
@@ -1168,7 +1291,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_h; ga.out = E->ll_qkv; ga.xp = E->xp[0]; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y;
             ga.ln = 1; ga.epi = EPI_QKV; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr;
+            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr; ga.kind = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(0, 1);
@@ -1188,11 +1311,11 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         PHASE_DONE();
         if (l == 1) PROF3(1, 0);
         {
-            const AttnGeom geo = attn_geom(E, LD, t);
-            const int ns = attn_nsplit(E, B, geo.R - ((geo.R > 0 && geo.cur) ? 1 : 0));
+            const AttnGeom geo = attn_geom(E, LD, t, PM, PD);
+            const int ns = attn_nsplit(E, GMAX, geo.R - ((geo.R > 0 && geo.cur) ? 1 : 0));
             for (int it = c; it < B * E->H * ns; it += G) {
-                const int s = it % ns, bh = it / ns;
-                attn_item(LD, bh / E->H, bh % E->H, s, ns, geo, (int)nph, fl, pre && it == c);
+                const int bh = div_small(it, ns), s = it - bh * ns, ib = bh / E->H;
+                attn_item(LD, ib, bh - ib * E->H, s, ns, geo, (int)nph, fl, pre && it == c);
                 consumer_sync();           // tile / q regions are reused by the next item or the next phase
             }
         }
@@ -1204,7 +1327,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_a; ga.out = E->ll_x1; ga.xp = E->xp[1]; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y;
             ga.ln = 0; ga.epi = EPI_PROJ; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 1);
+            ga.ln_out = LN_BLOCK(2 * l + 1); ga.kind = 1;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(2, 1);
@@ -1215,7 +1338,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_x1; ga.out = E->ll_g; ga.xp = E->xp[2]; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y;
             ga.ln = 1; ga.epi = EPI_FC; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr;
+            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr; ga.kind = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(3, 1);
@@ -1228,7 +1351,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_g; ga.out = E->ll_h; ga.xp = E->xp[3]; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y;
             ga.ln = 0; ga.epi = EPI_PROJ2; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl + 1;
             ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 2);
+            ga.ln_out = LN_BLOCK(2 * l + 2); ga.kind = 2;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(4, 1);
@@ -1236,12 +1359,12 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
     if (A.h_out) {      // Transformer.forward boundary: this CTA's slice of the residual stream
         const ushort2 wc = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * ((depth - 1) & 1) + 128)[1];
-        const int ppc = (wc.y * 4) / KS;
+        const int ppc = (wc.y * 4) >> E->ks_shift;
         const float2* res = sm_res();
-        for (int e = tid; e < B * ppc; e += kConsumers) {
-            const int b = e / ppc, pl = e - b * ppc;
-            const int col = wc.x * 8 + 2 * (rank * ppc + pl);
-            *reinterpret_cast<float2*>(A.h_out + (size_t)b * W + col) = res[b * 32 + pl];
+        const int lane = tid & 31;
+        for (int b = warp; b < B && lane < ppc; b += 8) {
+            const int col = wc.x * 8 + 2 * (rank * ppc + lane);
+            *reinterpret_cast<float2*>(A.h_out + (size_t)b * W + col) = res[b * 32 + lane];
         }
     }
     if (do_logits) logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
@@ -1249,7 +1372,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     CLEAR_AFTER(2 * depth - 1, 2 * depth);
     if (c == 0) {
         consumer_sync();
-        if (tid < 32) LN_BLOCK(2 * depth)[16 * tid] = 0;
+        if (tid < 32) LN_BLOCK(2 * depth)[16 * (tid >> 1) + (tid & 1)] = 0;
         if (tid == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1260,6 +1383,9 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
 #undef LN_BLOCK
 #undef CLEAR_AFTER
+#undef PM
+#undef PD
+#undef GMAX
 #undef PHASE_DONE
 #undef PROF3
 }
@@ -1505,7 +1631,7 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     L.off_qkv = off; off = align_up(off + (size_t)16 * 3 * c.n_state * 4, 256);
     L.off_a = off;   off = align_up(off + (size_t)16 * c.n_state * 4, 256);
     L.off_g = off;   off = align_up(off + (size_t)16 * c.mlp_width * 4, 256);
-    for (int gi = 0; gi < 4; ++gi) { L.off_xp[gi] = off; off = align_up(off + (size_t)G * 16 * kXpCols * 8, 256); }
+    for (int gi = 0; gi < 4; ++gi) { L.off_xp[gi] = off; off = align_up(off + (size_t)G * 8 * 16 * kXpCols * 8, 256); }
     L.off_part = off; off = align_up(off + (size_t)c.max_batch * c.heads * kMaxSplit * (L.dh_pad + 2) * 4, 256);
     L.off_acnt = off; off = align_up(off + (size_t)c.max_batch * c.heads * 4, 256);
     L.off_prof = off; off = align_up(off + (size_t)kProfSlots * 8, 256);
@@ -1601,8 +1727,13 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     E.W = cfg->width; E.S = cfg->n_state; E.M = cfg->mlp_width; E.H = cfg->heads; E.dh = L.dh; E.dh_pad = L.dh_pad;
     E.L = cfg->n_ctx; E.blocks = cfg->blocks; E.bc = L.bc; E.bins = cfg->bins; E.prime_pad = L.prime_pad;
     E.enc_dims = cfg->encoder_dims; E.Bmax = cfg->max_batch; E.add_cond_after = cfg->add_cond_after;
-    E.depth = cfg->depth; E.G = G; E.KS = L.KS; E.U = L.U; E.RC = L.RC; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
+    E.depth = cfg->depth; E.G = G; E.KS = L.KS; E.ks_shift = L.KS == 4 ? 2 : L.KS == 2 ? 1 : 0; E.U = L.U; E.RC = L.RC; E.nslot = L.nslot; E.uni_bytes = L.uni_bytes; E.kvpre_bytes = L.kvpre_bytes; E.small_bytes = (int)L.small_per_layer; E.prof_on = getenv("JK_PROFILE") ? 1 : 0;
     E.kv_prefetch = getenv("JK_KV_PREFETCH") ? atoi(getenv("JK_KV_PREFETCH")) : 1;
+    E.xp_direct = getenv("JK_XP_DIRECT") ? atoi(getenv("JK_XP_DIRECT")) : 0;
+    {
+        const int nowait = getenv("JK_NOWAIT") ? atoi(getenv("JK_NOWAIT")) : 0;
+        JK_CHECK_CUDA(cudaMemcpyToSymbol(jk_nowait, &nowait, sizeof(int)));
+    }
     {   // reference: scale = 1/sqrt(sqrt(dh)); w.mul_(scale*scale)  (factored_attention.py:83-88)
         double sc = 1.0 / sqrt(sqrt((double)L.dh));
         E.scale2 = (float)(sc * sc);

@@ -20,8 +20,9 @@ struct LayerDev {
 struct EngineDev {
     int W, S, M, H, dh, dh_pad, L, blocks, bc, bins, prime_pad, enc_dims, Bmax, add_cond_after, depth, G;
     int RC;                         // rows of one shared-memory K (or V) tile of the attention phase
+    int ks_shift;                   // log2(KS)
     int KS, U;                      // K-split factor of every Conv1D and the number of column units (G = U * KS)
-    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on, kv_prefetch;
+    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on, kv_prefetch, xp_direct;
     float scale2;
     const ushort2* cols;            // [U][depth][4] : (first 8-column group, number of groups) of a unit
     const uint8_t* streams;
