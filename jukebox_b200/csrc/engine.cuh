@@ -22,7 +22,7 @@ struct EngineDev {
     int RC;                         // rows of one shared-memory K (or V) tile of the attention phase
     int ks_shift;                   // log2(KS)
     int KS, U;                      // K-split factor of every Conv1D and the number of column units (G = U * KS)
-    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on, kv_prefetch, xp_direct;
+    int nslot, uni_bytes, kvpre_bytes, small_bytes, prof_on, kv_prefetch;
     float scale2;
     const ushort2* cols;            // [U][depth][4] : (first 8-column group, number of groups) of a unit
     const uint8_t* streams;

@@ -82,12 +82,22 @@ class _NameTables:
         s = ''.join(c if c.isascii() and c.isalnum() else '_' for c in s.lower())
         return re.sub(r'_+', '_', s).strip('_')
 
+    def _lookup(self, table, key, kind):
+        """id of `key`; unknown names map to id 0 ("unknown") WITH a warning, as the reference prints one
+        (data/artist_genre_processor.py) - a silent 0 would give plausible but mis-conditioned samples"""
+        if key in table:
+            return table[key]
+        if key not in ("unknown", ""):
+            why = "no id tables loaded: set JUKEBOX_IDS_DIR" if not table else "not in the id table"
+            print(f"Input {kind} {key!r} maps to unknown ({why})")
+        return 0
+
     def artist(self, name):
-        return self.artist_ids.get(name.lower() if self.v3 else self._norm(name), 0)
+        return self._lookup(self.artist_ids, name.lower() if self.v3 else self._norm(name), "artist")
 
     def genres(self, name):
         words = [name.lower()] if self.v3 else self._norm(name).split('_')
-        return [self.genre_ids.get(w, 0) for w in words]
+        return [self._lookup(self.genre_ids, w, "genre") for w in words]
 
 
 class Labeller:

@@ -1,5 +1,5 @@
 """Hyper-parameter registry: same names, same resolved values and the same `setup_hparams`
-semantics as the reference (jukebox/hparams.py) - tests/test_hparams.py compares every resolved set
+semantics as the reference (jukebox/hparams.py) - tests/test_host_cpu.py compares every resolved set
 against a dump of the reference's registry (tests/golden/hparams.json).
 """
 

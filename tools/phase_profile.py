@@ -72,6 +72,15 @@ def main():
             rows.append([(s1 - s0), (s2 - s1), (s3 - s2), (s4 - s3)])
         r = np.mean(rows, 0) / mhz
         print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}")
+    print("  CTA 0, staging detail (us from phase entry): statistics ready | own polled loads in | past the statistics barrier | staged + barrier")
+    for j, nm in ((0, "LN+QKV"), (2, "proj"), (3, "LN+FC"), (4, "proj2")):
+        rows = []
+        for l in range(depth):
+            slot = 1 + 5 * l + j
+            s0 = p2[slot, 0]
+            rows.append([p2[slot, 5] - s0, p2[slot, 6] - s0, p2[slot, 7] - s0, p2[slot, 1] - s0])
+        r = np.mean(rows, 0) / mhz
+        print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}")
     sel = [l for l in range(depth) if funcs[l] in (1, 3) and p2[1 + 5 * l + 1, 3] > 0]
     if sel:
         ar = np.array([[p2[1 + 5 * l + 1, i] for i in (0, 1, 2, 3)] for l in sel]) / mhz
