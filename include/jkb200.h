@@ -249,6 +249,48 @@ int jk_layernorm_f32(const float* x, const float* g, const float* b, float* y, i
 int jk_embedding_f32(const int64_t* idx, const float* table, const float* add, float* out, int64_t n,
                      int rows, int width, jk_stream_t stream);
 
+/* ---- fp32 transformer path (not the hot path: exactness against the reference's fp32 outputs) ------------------------
+ * Transformer.forward in fp32 (transformer/transformer.py:169-192): sample = forward mode over a whole sequence
+ * (training-shaped calls, alignment with record_attn - prior/prior.py:327-344) and sampling with fp32 K/V caches
+ * (ConditionalAutoregressive2D.sample(fp16=False), prior/autoregressive.py:199-249).  One structure per layer holds the
+ * reference's parameter tensors (fp32, Conv1D layout [n_in, n_out], transformer/ops.py:83-101) and the layer's caches. */
+typedef struct jk_f32_layer {
+    const float *ln0_g, *ln0_b, *ln1_g, *ln1_b;
+    const float *c_attn_w, *c_attn_b;       /* [width, 3 n_state]; [width, n_state] (c_attn of an enc-dec layer) */
+    const float *c_enc_kv_w, *c_enc_kv_b;   /* [width, 2 n_state], attn_func 6 only */
+    const float *c_proj_w, *c_proj_b;       /* [n_state, width] */
+    const float *fc_w, *fc_b;               /* [width, mlp_width] */
+    const float *proj2_w, *proj2_b;         /* [mlp_width, width] */
+    float *k_cache, *v_cache;               /* [n, n_ctx, n_state] ([n, encoder_dims, n_state] for attn_func 6); rows are
+                                               absolute positions.  Forward mode passes scratch of the same shape. */
+    float *attn_w;                          /* optional: attention weights [n, heads, P, n_ctx | encoder_dims] of this call
+                                               (record_attn, factored_attention.py:100-102), or NULL */
+    int32_t attn_func;                      /* 0, 1, 2, 3, 6, 7 (factored_attention.py:49-58) */
+} jk_f32_layer;
+
+typedef struct jk_f32_args {
+    int32_t n, P, p0;              /* samples, positions in this call, absolute position of the first one */
+    int32_t width, n_state, mlp_width, heads, n_ctx, blocks, prime_len, encoder_dims, depth;
+    float* x;                      /* [n, P, width]: residual stream, transformed in place */
+    const float* encoder_kv;       /* [n, encoder_dims, width] or NULL (read when p0 == 0) */
+    float* work;                   /* jk_f32_workspace_floats() floats */
+} jk_f32_args;
+
+int jk_f32_workspace_floats(const jk_f32_args* a, size_t* floats);
+/* Positions [p0, p0 + P) of every sample through all `depth` layers.  K / V of the new positions are written to the
+ * caches first, each query then attends the cache rows of its pattern; a call with p0 = 0, P = n_ctx is the reference's
+ * forward mode, P = 1 its per-token sampling step. */
+int jk_f32_forward(const jk_f32_args* a, const jk_f32_layer* layers, jk_stream_t stream);
+/* x[b, i, :] = (position p0+i == 0 ? y_cond[b] or start_token : x_emb[tokens[b, p0+i-1]]) + pos_emb[p0+i] (+ x_cond)
+ * (prior/autoregressive.py:115-123 shifted input in forward mode, :176-191 get_emb in sampling). x_cond_len: 0 = none,
+ * 1 = one broadcast row per sample, else rows indexed by position. */
+int jk_f32_embed(float* x, const int64_t* tokens, int64_t tok_stride, const float* y_cond, const float* x_cond,
+                 int64_t x_cond_len, const float* x_emb, const float* pos_emb, const float* start_token, int n, int P,
+                 int p0, int width, jk_stream_t stream);
+/* y[M, N] = x[M, K] . w + b;  w is [K, N] (Conv1D) or, with w_is_nk, [N, K] (nn.Linear: x_out, autoregressive.py:86) */
+int jk_f32_linear(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int w_is_nk,
+                  jk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

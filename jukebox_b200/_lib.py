@@ -34,6 +34,20 @@ class PlanInfo(C.Structure):
                 ("tile_rows", C.c_int32), ("arena_bytes", C.c_uint64), ("stream_stride", C.c_uint64)]
 
 
+class F32Layer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("ln0_g", "ln0_b", "ln1_g", "ln1_b", "c_attn_w", "c_attn_b", "c_enc_kv_w", "c_enc_kv_b",
+                 "c_proj_w", "c_proj_b", "fc_w", "fc_b", "proj2_w", "proj2_b", "k_cache", "v_cache", "attn_w")] + \
+               [("attn_func", C.c_int32)]
+
+
+class F32Args(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("n", "P", "p0", "width", "n_state", "mlp_width", "heads", "n_ctx", "blocks", "prime_len",
+                 "encoder_dims", "depth")] + \
+               [("x", C.c_void_p), ("encoder_kv", C.c_void_p), ("work", C.c_void_p)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("x_in", C.c_void_p), ("tokens", C.c_void_p),
                 ("tok_stride", C.c_int64), ("y_cond", C.c_void_p), ("x_cond", C.c_void_p),
@@ -86,6 +100,10 @@ SIGNATURES = {
     "jk_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "jk_layernorm_f32": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "jk_embedding_f32": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
+    "jk_f32_workspace_floats": (_I, [C.POINTER(F32Args), C.POINTER(C.c_size_t)]),
+    "jk_f32_forward": (_I, [C.POINTER(F32Args), C.POINTER(F32Layer), _P]),
+    "jk_f32_embed": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "jk_f32_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjkb200.so")
 STAMP = os.path.join(HERE, ".libjkb200.stamp")
-SOURCES = ["api.cu", "decode_engine.cu", "prefill.cu", "prefill_gemm.cu", "sampling.cu", "vqvae_kernels.cu"]
+SOURCES = ["api.cu", "decode_engine.cu", "f32_path.cu", "prefill.cu", "prefill_gemm.cu", "sampling.cu", "vqvae_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", 
               "-Xcompiler", "-Wno-unused-function", "--expt-relaxed-constexpr", "-rdc=false"]

@@ -166,10 +166,6 @@ __device__ __forceinline__ unsigned long long wait_stat_word(const long long* p,
     return w;
 }
 
-__device__ __forceinline__ float ld_half_cg(const __half* p) {
-    return __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))));
-}
-
 // quick_gelu(x) = x * sigmoid(1.702 x) (transformer/ops.py:33-35).  The reference's eager fp16 path
 // rounds after each of its three elementwise ops; restated exactly so (x is already an fp16 value).
 __device__ __forceinline__ float quick_gelu_f(float x) {
@@ -1568,11 +1564,15 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
         L.off_encx = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * c.width * 2, 1024);
         L.off_ency = off; if (any6) off = align_up(off + (size_t)c.max_batch * c.encoder_dims * 2 * c.n_state * 2, 1024);
     }
-    {   // chunked prefill: K-major fp16 weight copies + activation workspace (prefill.cu).  Needs every GEMM K to
-        // be a multiple of the tcgen05 K block (64) and no encoder-decoder layer; else pf_rows = 0.
-        bool ok = (c.width % 64 == 0) && (c.n_state % 64 == 0) && (c.mlp_width % 64 == 0) && !getenv("JK_NO_PREFILL");
-        for (int l = 0; l < depth; ++l) ok = ok && (c.attn_func[l] != 6);
-        L.pf_len = ok ? std::min(c.n_ctx, 512) : 0;
+    {   // chunked prefill: K-major fp16 weight copies + activation workspace (prefill.cu).  Every GEMM K must give
+        // 16-byte rows (K % 8) and fill at least one tcgen05 K block; K tails are zero-filled by TMA.  The workspace
+        // holds a whole window (n_ctx positions x max_batch: 2.8 GB for 1b_lyrics - 180 GB of HBM is there to be used),
+        // so continuation windows re-prime their 4096 given tokens in one pass; JK_PREFILL_MAX lowers it.
+        auto k_ok = [](int k) { return k >= 64 && k % 8 == 0; };
+        const bool ok = k_ok(c.width) && k_ok(c.n_state) && k_ok(c.mlp_width) && !getenv("JK_NO_PREFILL");
+        int cap = c.n_ctx;
+        if (const char* e = getenv("JK_PREFILL_MAX")) cap = std::max(2, std::min(cap, atoi(e)));
+        L.pf_len = ok ? cap : 0;
         L.pf_rows = c.max_batch * L.pf_len;
         L.wt_per_layer = align_up((size_t)(3 * c.n_state * c.width + c.width * c.n_state + 2 * c.mlp_width * c.width) * 2, 1024);
         L.off_wt = off; if (ok) off = align_up(off + L.wt_per_layer * depth, 1024);
@@ -1830,7 +1830,7 @@ extern "C" int jk_prior_set_encoder_kv(jk_prior* p, const float* encoder_kv, int
     const jk_prior_config& c = p->cfg;
     JK_REQUIRE(n >= 1 && n <= c.max_batch, "n_samples out of range");
     const int rows = n * c.encoder_dims;
-    JK_REQUIRE(c.width % 64 == 0, "encoder-decoder layers need width %% 64 == 0 (tcgen05 K block)");
+    JK_REQUIRE(c.width >= 64 && c.width % 8 == 0, "encoder-decoder layers need width >= 64 and width %% 8 == 0 (tcgen05 GEMM operand rows)");
     {   // encoder_kv.type_as(x): fp32 -> fp16 once, shared by every enc-dec layer
         const size_t cnt = (size_t)rows * c.width;
         to_half_kernel<float><<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(encoder_kv, p->enc_x16, cnt);

@@ -17,6 +17,7 @@
 // Afterwards the engine stands at position P exactly as if P decode steps had run: only the K/V caches and
 // the position carry over between steps.
 #include "engine.cuh"
+#include <algorithm>
 
 using namespace jk;
 
@@ -79,12 +80,14 @@ __global__ void ln_rows_kernel(const __half* __restrict__ x, const float* __rest
 // One CTA per (position p, head h, sample b).  Keys of p by pattern (all inside [0, P)):
 //   0 dense: 0..p     1 block: block start..p     2 transpose: p % bc + j*bc, j = 0..p/bc
 //   3 previous block: (p/bc - 1)*bc .. +bc-1 (none in the first block -> output 0)     7 prime: 0..p (p < prime)
+//   6 encoder-decoder: every encoder row; K / V come from the layer's cache (jk_prior_set_encoder_kv), q from c_attn
 // Scores fp16(fp16(q.k) * dh^-1/2), softmax fp32, P rounded to fp16 (unnormalised), P.V fp32, / sum - the
 // decode kernel's order of roundings.
 struct AttnFwd {
-    const __half* qkv;   // [n*P][3S]
+    const __half* qkv;   // [n*P][q_stride]: q | k | v per row (q only for an encoder-decoder layer)
     __half* a;           // [n*P][S]
-    int P, S, H, dh, bc, attn_func, prime;
+    const __half *kc, *vc;   // encoder-decoder layers: the layer's K / V cache [n][H][enc_rows][dhp]
+    int P, S, H, dh, bc, attn_func, prime, q_stride, enc_rows, dhp;
     float scale2;
 };
 
@@ -94,6 +97,7 @@ __device__ __forceinline__ int fwd_nkeys(const AttnFwd& A, int p) {
         case 1: return p % A.bc + 1;
         case 2: return p / A.bc + 1;
         case 3: return p >= A.bc ? A.bc : 0;
+        case 6: return A.enc_rows;
         case 7: return p < A.prime ? p + 1 : A.prime;
     }
     return 0;
@@ -118,8 +122,12 @@ __global__ void __launch_bounds__(kFwdThreads) attn_fwd_kernel(AttnFwd A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dh = A.dh, S = A.S;
     const size_t row = (size_t)b * A.P + p;
-    const __half* q = A.qkv + row * 3 * S + h * dh;
+    const __half* q = A.qkv + row * A.q_stride + h * dh;
     __half* out = A.a + row * S + h * dh;
+    const bool enc = A.attn_func == 6;
+    const __half* kbase = enc ? A.kc + ((size_t)b * A.H + h) * A.enc_rows * A.dhp : A.qkv + (size_t)b * A.P * 3 * S + S + h * dh;
+    const __half* vbase = enc ? A.vc + ((size_t)b * A.H + h) * A.enc_rows * A.dhp : kbase + S;
+    const size_t kstride = enc ? (size_t)A.dhp : (size_t)3 * S;
     const int nk = fwd_nkeys(A, p);
     if (nk == 0) {
         for (int d = tid; d < dh; d += kFwdThreads) out[d] = __float2half_rn(0.f);
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(kFwdThreads) attn_fwd_kernel(AttnFwd A) {
     for (int d = tid; d < dh; d += kFwdThreads) qs[d] = ldh(q + d);
     __syncthreads();
     for (int j = warp; j < nk; j += kFwdThreads / 32) {
-        const __half* k = A.qkv + ((size_t)b * A.P + fwd_key(A, p, j)) * 3 * S + S + h * dh;
+        const __half* k = kbase + (size_t)fwd_key(A, p, j) * kstride;
         float dot = 0.f;
         for (int d = lane; d < dh; d += 32) dot = fmaf(qs[d], ldh(k + d), dot);
         dot = warp_sum(dot);
@@ -155,8 +163,7 @@ __global__ void __launch_bounds__(kFwdThreads) attn_fwd_kernel(AttnFwd A) {
     for (int d = tid; d < dh; d += kFwdThreads) {
         float o = 0.f;
         for (int j = 0; j < nk; ++j) {
-            const __half* v = A.qkv + ((size_t)b * A.P + fwd_key(A, p, j)) * 3 * S + 2 * S + h * dh;
-            o = fmaf(sc[j], ldh(v + d), o);
+            o = fmaf(sc[j], ldh(vbase + (size_t)fwd_key(A, p, j) * kstride + d), o);
         }
         out[d] = __float2half_rn(o * inv);
     }
@@ -207,8 +214,8 @@ extern "C" int jk_prior_prefill(jk_prior* p, const jk_prefill_args* a, jk_stream
     JK_REQUIRE(p && a, "null argument");
     const jk_prior_config& c = p->cfg;
     const EngineDev& E = p->host;
-    JK_REQUIRE(p->pf_len > 0, "this configuration has no chunked prefill (needs width, n_state, mlp_width %% 64 == 0 and no "
-                              "encoder-decoder layers): step the given tokens through jk_prior_step");
+    JK_REQUIRE(p->pf_len > 0, "this configuration has no chunked prefill (needs width, n_state, mlp_width >= 64 and %% 8 == 0): "
+                              "step the given tokens through jk_prior_step");
     JK_REQUIRE(p->t_host == 0, "prefill starts at position 0 (engine is at %d)", p->t_host);
     const int n = a->n_samples, P = a->n_positions;
     JK_REQUIRE(n >= 1 && n <= c.max_batch, "n_samples %d out of range (max_batch %d)", n, c.max_batch);
@@ -227,7 +234,7 @@ extern "C" int jk_prior_prefill(jk_prior* p, const jk_prefill_args* a, jk_stream
     }
     const unsigned ln_grid = (unsigned)((rows + 7) / 8);
     static bool attr_set[64] = {};         // per device: the attribute belongs to the device's copy of the function
-    const size_t fwd_smem = (size_t)(E.dh + P) * 4;
+    const size_t fwd_smem = (size_t)(E.dh + std::max(P, E.enc_dims)) * 4;
     int dev = 0;
     JK_CHECK_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
@@ -239,14 +246,17 @@ extern "C" int jk_prior_prefill(jk_prior* p, const jk_prefill_args* a, jk_stream
         const LayerDev& LD = E.layer[l];
         ln_rows_kernel<<<ln_grid, 256, 0, stream>>>(p->pf_x, LD.ln0_g, LD.ln0_b, p->pf_xn, rows, W);
         JK_CHECK_CUDA(cudaGetLastError());
-        int rc = gemm_f16_tc(p->pf_xn, p->wt[0][l], LD.b_qkv, nullptr, p->pf_qkv, rows, 3 * S, W, 0, stream);
+        const bool enc = LD.attn_func == 6;       // c_attn gives q only; K / V are the encoder's (already in the cache)
+        const int q_stride = enc ? S : 3 * S;
+        int rc = gemm_f16_tc(p->pf_xn, p->wt[0][l], LD.b_qkv, nullptr, p->pf_qkv, rows, q_stride, W, 0, stream);
         if (rc) return rc;
         AttnFwd A;
         A.qkv = p->pf_qkv; A.a = p->pf_a; A.P = P; A.S = S; A.H = H; A.dh = E.dh; A.bc = E.bc; A.attn_func = LD.attn_func;
-        A.prime = E.prime_pad; A.scale2 = E.scale2;
+        A.prime = E.prime_pad; A.scale2 = E.scale2; A.q_stride = q_stride; A.kc = LD.kc; A.vc = LD.vc; A.enc_rows = E.enc_dims;
+        A.dhp = E.dh_pad;
         attn_fwd_kernel<<<dim3(P, H, n), kFwdThreads, fwd_smem, stream>>>(A);
         JK_CHECK_CUDA(cudaGetLastError());
-        {
+        if (!enc) {
             const size_t cnt = (size_t)rows * S;
             kv_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(p->pf_qkv, LD.kc, LD.vc, n, P, S, H, E.dh, E.dh_pad,
                                                                                   LD.rows, LD.attn_func, E.bc, E.blocks, E.prime_pad);

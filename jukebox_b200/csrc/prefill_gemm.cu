@@ -91,7 +91,7 @@ prefill_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb = K / BK;
+    const int nkb = (K + BK - 1) / BK;       // a K tail reads zeros: TMA zero-fills both operands beyond K
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -222,7 +222,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int K) {
 int jk::gemm_f16_tc(const void* x, const void* w_t, const float* bias, const void* res, void* y, int M, int N, int K,
                     int epi, cudaStream_t stream) {
     JK_REQUIRE(x && w_t && y, "null argument");
-    JK_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % BK == 0, "prefill GEMM needs K to be a multiple of %d (got M %d N %d K %d)", BK, M, N, K);
+    JK_REQUIRE(M >= 1 && N >= 1 && K >= BK && K % 8 == 0, "prefill GEMM needs K >= %d and K %% 8 == 0 (16-byte rows for TMA); got M %d N %d K %d", BK, M, N, K);
     JK_REQUIRE((((uintptr_t)x | (uintptr_t)w_t | (uintptr_t)y | (uintptr_t)res) & 15) == 0, "operands must be 16-byte aligned");
     JK_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || res), "bad epilogue");
     CUtensorMap mx, mw;

@@ -588,6 +588,201 @@ int launch_resblock_tc(const float* x, float* out, const float* w1, const float*
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same block with the fp16 x 3 split on mma.sync.m16n8k16 (the default decoder-side kernel).
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits, the same as the TF32 split (fp16 and TF32 both carry
+// 11 significant bits), products hi.w_hi + lo.w_hi + hi.w_lo accumulated in fp32.  Against 3xTF32: an MMA covers k = 16
+// instead of 8 at the same issue cost, operands are half the shared-memory bytes and arrive as whole fragments through
+// ldmatrix (A: [position][channel] rows, B: [k][n] rows with .trans) - 10 ldmatrix + 24 MMA per k16 step at C = 64 where the
+// TF32 kernel issued 32 LDS + 24 cvt/sub + 24 MMA for the same k range.  Values beyond the fp16 range saturate
+// (cvt.satfinite); VQ-VAE activations are O(1).  Small activations lose nothing that matters: an fp16 remainder below
+// 2^-14 is kept to an ABSOLUTE 2^-25.
+//   * ONE WARP PER 16-POSITION TILE: a warp's output rows need only its own rows of the three tap tiles and of the hidden
+//     tile, so nothing is shared between warps except the weights - no CTA barrier in the tile loop, and the eight warps of
+//     a CTA drift apart so that one's global loads overlap another's MMAs
+//   * persistent CTAs (grid = #SMs), W1 / W2 hi + lo planes staged once per CTA
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
+    unsigned short h, l;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    hi = __ushort_as_half(h);
+    const float r = x - __half2float(hi);
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(r));
+    lo = __ushort_as_half(l);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_h(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// weights are split after an exact scaling by 2^8 (undone in the epilogues): a typical |w| ~ 0.05 has its fp16 remainder
+// (~2e-5) in the subnormal range, where the split would keep only ~19 bits
+constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;
+
+template <int C>
+struct ResH2 {
+    static constexpr int XS = C + 8;                       // halfs per row: 16-byte aligned rows an odd number of 16-byte units apart
+    static constexpr int NT = C / 8, WARPS = 8;
+    static constexpr int w_halfs = 2 * (3 * C + C) * XS;   // W1 hi, W1 lo, W2 hi, W2 lo
+    static constexpr int warp_halfs = 2 * 3 * 16 * XS;     // a warp's tap tiles, hi and lo; the hidden tile reuses tap 0
+    static constexpr size_t smem = (size_t)(w_halfs + WARPS * warp_halfs) * 2;
+};
+
+// acc[nt] += A(16 x 16 at `ah`/`al`) . B(16 x C at `bh`/`bl`), three products of the split
+template <int C>
+__device__ __forceinline__ void h2_kstep(float (&acc)[C / 8][4], const __half* ah, const __half* al, const __half* bh, const __half* bl,
+                                         int lane) {
+    constexpr int XS = ResH2<C>::XS;
+    const int r = lane & 15, c8 = (lane >> 4) * 8;
+    uint32_t fh[4], fl[4];
+    ldsm_x4(fh, ah + r * XS + c8);
+    ldsm_x4(fl, al + r * XS + c8);
+#pragma unroll
+    for (int np = 0; np < C / 16; ++np) {
+        uint32_t wh[4], wl[4];
+        ldsm_x4_t(wh, bh + r * XS + np * 16 + c8);
+        ldsm_x4_t(wl, bl + r * XS + np * 16 + c8);
+        mma_h(acc[2 * np], fl, wh[0], wh[1]);
+        mma_h(acc[2 * np], fh, wl[0], wl[1]);
+        mma_h(acc[2 * np], fh, wh[0], wh[1]);
+        mma_h(acc[2 * np + 1], fl, wh[2], wh[3]);
+        mma_h(acc[2 * np + 1], fh, wl[2], wl[3]);
+        mma_h(acc[2 * np + 1], fh, wh[2], wh[3]);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 1)
+resblock_h2_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w1,
+                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                   long long T, int dil, float rs, long long tiles_per_clip, long long total_tiles) {
+    constexpr int XS = ResH2<C>::XS, NT = ResH2<C>::NT;
+    extern __shared__ __align__(16) __half hsm[];
+    __half* w1h = hsm;                          // [3 C][XS]
+    __half* w1l = w1h + 3 * C * XS;
+    __half* w2h = w1l + 3 * C * XS;             // [C][XS]
+    __half* w2l = w2h + C * XS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __half* xh = w2l + C * XS + warp * ResH2<C>::warp_halfs;      // [3][16][XS] relu(x) at t + (tap - 1) * dil
+    __half* xl = xh + 3 * 16 * XS;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int i = tid; i < 3 * C * C; i += 256) {
+        const int o = (i / C) * XS + i % C;
+        split_h2(kWScale * __ldg(w1 + i), w1h[o], w1l[o]);
+    }
+    for (int i = tid; i < C * C; i += 256) {
+        const int o = (i / C) * XS + i % C;
+        split_h2(kWScale * __ldg(w2 + i), w2h[o], w2l[o]);
+    }
+    __syncthreads();
+    constexpr int TX = C / 4, PER = 16 * TX / 32;         // float4 loads per lane per tap tile
+#pragma unroll 1
+    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < total_tiles; tile += (long long)gridDim.x * 8) {
+        const long long nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * 16;
+        const float* xin = x + (size_t)nb * T * C;
+        float* xout = out + (size_t)nb * T * C;
+        __syncwarp();                           // the previous tile's fragment reads are done
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+            const long long off = (long long)(tap - 1) * dil;
+            float4 v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = lane + 32 * j, tt = i / TX, c4 = i % TX;
+                const long long tp = t0 + tt + off;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tp >= 0 && tp < T) v[j] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)tp * C) + c4);
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = lane + 32 * j, tt = i / TX, c4 = i % TX;
+                __half h[4], l[4];
+                split_h2(fmaxf(v[j].x, 0.f), h[0], l[0]);
+                split_h2(fmaxf(v[j].y, 0.f), h[1], l[1]);
+                split_h2(fmaxf(v[j].z, 0.f), h[2], l[2]);
+                split_h2(fmaxf(v[j].w, 0.f), h[3], l[3]);
+                *reinterpret_cast<uint2*>(xh + (tap * 16 + tt) * XS + c4 * 4) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(xl + (tap * 16 + tt) * XS + c4 * 4) = *reinterpret_cast<const uint2*>(l);
+            }
+        }
+        __syncwarp();
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+            for (int k16 = 0; k16 < C / 16; ++k16)
+                h2_kstep<C>(acc, xh + tap * 16 * XS + k16 * 16, xl + tap * 16 * XS + k16 * 16,
+                            w1h + (tap * C + k16 * 16) * XS, w1l + (tap * C + k16 * 16) * XS, lane);
+        __syncwarp();                           // tap tile 0 is dead: the hidden tile takes its place
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {       // hidden = relu(conv1 + b1), split, -> shared memory (this warp's rows only)
+            const int col = nt * 8 + 2 * t4;
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(b1 + col));
+            __half h[2], l[2];
+            split_h2(fmaxf(fmaf(acc[nt][0], kWInv, bv.x), 0.f), h[0], l[0]);
+            split_h2(fmaxf(fmaf(acc[nt][1], kWInv, bv.y), 0.f), h[1], l[1]);
+            *reinterpret_cast<uint32_t*>(xh + g * XS + col) = *reinterpret_cast<const uint32_t*>(h);
+            *reinterpret_cast<uint32_t*>(xl + g * XS + col) = *reinterpret_cast<const uint32_t*>(l);
+            split_h2(fmaxf(fmaf(acc[nt][2], kWInv, bv.x), 0.f), h[0], l[0]);
+            split_h2(fmaxf(fmaf(acc[nt][3], kWInv, bv.y), 0.f), h[1], l[1]);
+            *reinterpret_cast<uint32_t*>(xh + (g + 8) * XS + col) = *reinterpret_cast<const uint32_t*>(h);
+            *reinterpret_cast<uint32_t*>(xl + (g + 8) * XS + col) = *reinterpret_cast<const uint32_t*>(l);
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k16 = 0; k16 < C / 16; ++k16)
+            h2_kstep<C>(acc, xh + k16 * 16, xl + k16 * 16, w2h + k16 * 16 * XS, w2l + k16 * 16 * XS, lane);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {       // out = x + res_scale * (conv2 + b2): x exact from global memory
+            const int col = nt * 8 + 2 * t4;
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(b2 + col));
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const long long t = t0 + g + 8 * hlf;
+                if (t < T) {
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(xin + (size_t)t * C + col));
+                    float2 v;
+                    v.x = rs * fmaf(acc[nt][2 * hlf], kWInv, bv.x); v.x += r.x;
+                    v.y = rs * fmaf(acc[nt][2 * hlf + 1], kWInv, bv.y); v.y += r.y;
+                    *reinterpret_cast<float2*>(xout + (size_t)t * C + col) = v;
+                }
+            }
+        }
+    }
+}
+
+template <int C>
+int launch_resblock_h2(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
+                       int n, long long T, int dil, float rs, cudaStream_t stream) {
+    constexpr size_t smem = ResH2<C>::smem;
+    static bool attr_set[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        JK_CHECK_CUDA(cudaFuncSetAttribute(resblock_h2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JK_CHECK_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+        attr_set[dev & 63] = true;
+    }
+    const long long per_clip = (T + 15) / 16, total = per_clip * n;
+    const unsigned grid = (unsigned)std::min<long long>((total + 7) / 8, sms[dev & 63]);
+    resblock_h2_kernel<C><<<grid, 256, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs, per_clip, total);
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // c_out <= 4 (the decoder's final Conv1d(emb_width -> 1 audio channel, k3), encdec.py:109): one thread per output
 // position, weights in shared memory.  The 64 x 64 tile kernel would spend 63/64 of its FMAs on padding here;
 // this one is a stream over the input (HBM bound).  Same accumulation order as the tile kernel (tap, then channel).
@@ -764,8 +959,13 @@ extern "C" int jk_resblock_tc(const float* x, float* out, const float* w1, const
                               int n, int64_t T, int C, int dilation, float res_scale, jk_stream_t stream) {
     JK_REQUIRE(x && out && w1 && w2 && b1 && b2, "null argument");
     JK_REQUIRE(x != out && T > 0 && n > 0, "x and out must differ, T and n must be positive");
-    if (C == 64) return launch_resblock_tc<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
-    if (C == 32) return launch_resblock_tc<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    static const bool tf32 = getenv("JK_RESBLOCK_TF32") != nullptr;      // the round-2 3xTF32 kernel, kept for A/B runs
+    if (tf32) {
+        if (C == 64) return launch_resblock_tc<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+        if (C == 32) return launch_resblock_tc<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    }
+    if (C == 64) return launch_resblock_h2<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
+    if (C == 32) return launch_resblock_h2<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
     JK_REQUIRE(false, "jk_resblock_tc: C must be 32 or 64 (got %d)", C);
     return 0;
 }

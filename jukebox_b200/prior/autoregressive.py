@@ -11,6 +11,7 @@ front of it) - nothing synchronises with the host inside the loop (the reference
 import numpy as np
 import torch as t
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..transformer.ops import filter_logits_scaled, sample_categorical
 from ..transformer.transformer import Transformer
@@ -124,8 +125,9 @@ class ConditionalAutoregressive2D(nn.Module):
 
     def _run(self, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p, get_preds, sample_tokens):
         """shared body of sample / primed_sample.  prime: LongTensor [N, P] of given tokens (P may be 0)."""
-        win = SamplingWindow(self, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p,
-                             get_preds, sample_tokens)
+        cls = SamplingWindow if fp16 else SamplingWindowF32
+        win = cls(self, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p, get_preds,
+                  sample_tokens)
         win.advance(win.sample_tokens)
         return win.finish()
 
@@ -148,33 +150,63 @@ class ConditionalAutoregressive2D(nn.Module):
 
     def forward(self, x, x_cond=None, y_cond=None, encoder_kv=None, fp16=False, loss_full=False, encode=False,
                 get_preds=False, get_acts=False, get_sep_loss=False):
-        """Only the `only_encode` use is built (the lyric encoder of separated enc-dec priors,
-        prior.py:285-301): returns activations [N, L, width].  The encoder is causal, so running it
-        through the decode engine position by position computes exactly the full forward pass."""
-        if not self.only_encode:
-            raise NotImplementedError("training forward / losses are out of scope; forward-mode attention "
-                                      "is the next hot-path row (SURVEY.md section 8f.1)")
-        if not fp16:
-            raise NotImplementedError("fp32 encoder path is not built; use fp16=True")
+        """Whole-sequence forward (reference autoregressive.py:116-172): the shifted token embeddings go through the
+        transformer in forward mode; returns the activations for an `only_encode` model (the lyric encoder of
+        separated enc-dec priors, prior.py:285-301), else (loss in bits per token, preds | acts | None).
+
+        fp16=True runs the causal stack through the fp16 decode engine (prefill kernels); fp16=False runs the fp32
+        forward-mode path (csrc/f32_path.cu).  No gradients: training is out of scope, the loss is an evaluation."""
         with t.no_grad():
             x = self.preprocess(x)
             N, D = x.shape
+            assert D == self.input_dims, f"forward runs whole sequences of {self.input_dims} tokens, got {D}"
             assert (0 <= x).all() and (x < self.bins).all()
             x_cond, y_cond = self._check_conds(N, x_cond, y_cond)
-            eng = self._engine(N)
-            self.transformer.del_cache()
-            acts = t.empty(N, D, self.width, dtype=t.float32, device=x.device)
             x = x.contiguous()
-            if 1 < D <= eng.prefill_capacity:
-                eng.prefill(N, D, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=acts)
+            if fp16 and not self.transformer._record_layers:
+                acts = self._acts_fp16(x, x_cond, y_cond, encoder_kv)
             else:
-                for i in range(D):
-                    out = t.empty(N, self.width, dtype=t.float32, device=x.device)
-                    eng.step(N, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=out)
-                    acts[:, i] = out
-            self.transformer.del_cache()
+                from ..transformer import f32
+                h = f32.embed(self, x, y_cond, x_cond, N, D, 0)
+                acts = self.transformer(h, encoder_kv=encoder_kv, fp16=False)
             if self.add_cond_after_transformer and x_cond is not None:
                 acts = acts + x_cond
+            if self.only_encode:
+                return acts
+            from ..transformer import f32
+            preds = f32.linear_nk(acts.view(N * D, self.width), self.x_out.weight).view(N, D, self.bins)
+            ln2 = float(np.log(2.))
+            if get_sep_loss:
+                assert self.prime_len is not None
+                pl = self.prime_len
+                loss = (F.cross_entropy(preds[:, :pl].reshape(-1, self.bins), x[:, :pl].reshape(-1)) / ln2,
+                        F.cross_entropy(preds[:, pl:].reshape(-1, self.bins), x[:, pl:].reshape(-1)) / ln2)
+            else:
+                loss = F.cross_entropy(preds.view(-1, self.bins), x.view(-1)) / ln2
+        if get_preds:
+            return loss, preds
+        if get_acts:
+            return loss, acts
+        return loss, None
+
+    def _acts_fp16(self, x, x_cond, y_cond, encoder_kv):
+        """the causal stack over given tokens on the fp16 decode engine: position by position it computes exactly the
+        forward pass (reference check_sample, factored_attention.py:424-455)"""
+        N, D = x.shape
+        eng = self._engine(N)
+        self.transformer.del_cache()
+        if any(b.attn_func == 6 for b in self.transformer._attn_mods):
+            assert encoder_kv is not None
+            eng.set_encoder_kv(encoder_kv)
+        acts = t.empty(N, D, self.width, dtype=t.float32, device=x.device)
+        if 1 < D <= eng.prefill_capacity:
+            eng.prefill(N, D, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=acts)
+        else:
+            for i in range(D):
+                out = t.empty(N, self.width, dtype=t.float32, device=x.device)
+                eng.step(N, tokens=x, y_cond=y_cond, x_cond=x_cond, h_out=out)
+                acts[:, i] = out
+        self.transformer.del_cache()
         return acts
 
 
@@ -191,8 +223,7 @@ class SamplingWindow:
                  sample_tokens):
         assert ca.training is False
         assert not ca.only_encode
-        if not fp16:
-            raise NotImplementedError("fp32 sampling is not built; use fp16=True (the reference's sampling_kwargs)")
+        assert fp16, "SamplingWindowF32 is the fp32 loop"
         self.ca = ca
         self.sample_tokens = ca.input_dims if sample_tokens is None else int(sample_tokens)
         self.N = N = n_samples
@@ -225,10 +256,19 @@ class SamplingWindow:
         self.pos = 0
         self.fbuf = None
         with t.no_grad():
-            if P > 1 and not get_preds and 1 < P <= eng.prefill_capacity:
+            if 1 < P <= eng.prefill_capacity:
                 # the given tokens go through all layers at once (the reference's chunked primed_sample,
-                # autoregressive.py:300-338); chunk_size is moot - one chunk
-                eng.prefill(N, P, tokens=self.tokens, y_cond=self.y_cond, x_cond=self.x_cond)
+                # autoregressive.py:300-338); chunk_size is moot - one chunk.  With get_preds their logits come from
+                # the same pass: x_out over (activations + cond) in fp32 (autoregressive.py:318-325)
+                if get_preds:
+                    from ..transformer import f32
+                    h = t.empty(N, P, ca.width, dtype=t.float32, device=dev)
+                    eng.prefill(N, P, tokens=self.tokens, y_cond=self.y_cond, x_cond=self.x_cond, h_out=h)
+                    if ca.add_cond_after_transformer and self.x_cond is not None:
+                        h = h + (self.x_cond[:, :P] if self.x_cond.shape[1] > 1 else self.x_cond)
+                    self.preds[:, :P] = f32.linear_nk(h.view(N * P, ca.width), ca.x_out.weight).view(N, P, ca.bins)
+                else:
+                    eng.prefill(N, P, tokens=self.tokens, y_cond=self.y_cond, x_cond=self.x_cond)
                 self.pos = P
 
     def advance(self, upto):
@@ -257,5 +297,67 @@ class SamplingWindow:
                 b.attn._advance(self.N, self.sample_tokens, self.fp16)
             tr.check_cache(self.N, self.sample_tokens, self.fp16)
             tr.del_cache()
+            x = self.ca.postprocess(self.tokens, self.sample_tokens)
+        return (x, self.preds) if self.get_preds else x
+
+
+class SamplingWindowF32:
+    """sample(fp16=False) / primed_sample(fp16=False): the same loop on the fp32 path (csrc/f32_path.cu) - embedding
+    row, all layers on fp32 K/V caches, + cond, x_out in fp32, then the shared filter / Categorical kernels.  Four C-ABI
+    calls per token instead of one persistent kernel: exactness path, not the hot path (train.py:139 sample logging)."""
+
+    def __init__(self, ca, n_samples, prime, x_cond, y_cond, encoder_kv, fp16, temp, top_k, top_p, get_preds,
+                 sample_tokens):
+        assert ca.training is False and not ca.only_encode and not fp16
+        self.ca = ca
+        self.sample_tokens = ca.input_dims if sample_tokens is None else int(sample_tokens)
+        self.N = N = n_samples
+        self.x_cond, self.y_cond = ca._check_conds(N, x_cond, y_cond)
+        self.P = P = prime.shape[1]
+        assert P < self.sample_tokens <= ca.input_dims, \
+            f"need given tokens {P} < sample_tokens {self.sample_tokens} <= input_dims {ca.input_dims}"
+        dev = ca.x_emb.weight.device
+        self.tr = ca.transformer
+        self.tr.del_cache()
+        self.encoder_kv = encoder_kv
+        self.tokens = t.zeros(N, self.sample_tokens, dtype=t.long, device=dev)
+        if P:
+            assert (0 <= prime).all() and (prime < ca.bins).all()
+            self.tokens[:, :P] = prime
+        self.get_preds = get_preds
+        self.preds = t.empty(N, self.sample_tokens, ca.bins, dtype=t.float32, device=dev) if get_preds else None
+        self.temp, self.top_k, self.top_p = temp, top_k, top_p
+        self.seed = int(t.empty((), dtype=t.int64).random_().item())
+        self.pos = 0
+        self.fbuf = None
+
+    def advance(self, upto):
+        from ..transformer import f32
+        ca, N, P, tokens = self.ca, self.N, self.P, self.tokens
+        upto = min(int(upto), self.sample_tokens)
+        with t.no_grad():
+            for sample_t in get_range(range(self.pos, upto)):
+                self.tr.check_cache(N, sample_t, False)
+                h = f32.embed(ca, tokens, self.y_cond, self.x_cond, N, 1, sample_t)
+                h = self.tr(h, encoder_kv=self.encoder_kv, sample=True, fp16=False)
+                if ca.add_cond_after_transformer and self.x_cond is not None:
+                    h = h + (self.x_cond[:, sample_t:sample_t + 1] if self.x_cond.shape[1] > 1 else self.x_cond)
+                if self.get_preds or sample_t >= P:
+                    x = f32.linear_nk(h.view(N, ca.width), ca.x_out.weight)
+                    if self.get_preds:
+                        self.preds[:, sample_t] = x
+                if sample_t >= P:
+                    if self.top_k or self.top_p:
+                        self.fbuf = filter_logits_scaled(x, self.temp, self.top_k, self.top_p, self.fbuf)
+                        sample_categorical(self.fbuf, 1.0, self.seed, sample_t, tokens)
+                    else:
+                        sample_categorical(x, self.temp, self.seed, sample_t, tokens)
+        self.pos = max(self.pos, upto)
+
+    def finish(self):
+        assert self.pos == self.sample_tokens, f"window stopped at {self.pos} of {self.sample_tokens}"
+        with t.no_grad():
+            self.tr.check_cache(self.N, self.sample_tokens, False)
+            self.tr.del_cache()
             x = self.ca.postprocess(self.tokens, self.sample_tokens)
         return (x, self.preds) if self.get_preds else x

@@ -13,16 +13,19 @@ the methods are written around two small helpers:
   LyricEncoder - the separate lyric encoder of an encoder-decoder prior: tokens -> activations -> projection ->
                  LayerNorm = the keys/values of the decoder's enc-dec attention layers (reference :285-301)
 
-Training entry points (z_forward, forward, losses) are out of scope and raise.
+z_forward / forward evaluate the loss (bits per token), predictions and recorded attention weights of a full window
+without gradients; optimisation itself is out of scope.
 """
 import numpy as np
 import torch as t
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ..utils import dist_adapter as dist
 from ..utils.dist_adapter import print_once
 from ..utils.torch_utils import assert_shape
 from ..transformer.ops import LayerNorm, Conv1D
+from ..transformer import f32
 from ..data.labels import EmptyLabeller, Labeller
 from ..vqvae.vqvae import calculate_strides
 from .autoregressive import ConditionalAutoregressive2D
@@ -268,13 +271,53 @@ class SimplePrior(nn.Module):
         acts = self.prime_prior(prime, None, None, None, fp16=fp16)
         assert_shape(acts, (N, self.prime_loss_dims, self.prime_acts_width))
         assert acts.dtype == t.float
-        w, b = self.prime_state_proj.w.float(), self.prime_state_proj.b.float()
-        states = t.addmm(b, acts.reshape(-1, self.prime_acts_width), w).view(N, self.prime_loss_dims, -1)
+        states = f32.linear_kn(acts.reshape(-1, self.prime_acts_width), self.prime_state_proj.w,
+                               self.prime_state_proj.b).view(N, self.prime_loss_dims, -1)
         kv = self.prime_state_ln(states)
         return kv.half() if (sample and fp16) else kv
 
-    def z_forward(self, *a, **k):
-        raise NotImplementedError("training / alignment forward is out of scope (SURVEY.md section 2.1 #3)")
+    def get_prime_loss(self, encoder_kv, prime_t):
+        """bits per lyric token of the encoder's next-token head (reference prior.py:303-310)"""
+        if not self.use_tokens:
+            return t.tensor(0.0, device=prime_t.device)
+        N, L, W = encoder_kv.shape
+        logits = f32.linear_nk(encoder_kv.float().reshape(N * L, W), self.prime_x_out.weight)
+        return F.cross_entropy(logits, prime_t.reshape(-1)) / float(np.log(2.))
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("training forward is out of scope (SURVEY.md section 2.1 #3)")
+    def z_forward(self, z, z_conds=[], y=None, fp16=False, get_preds=False, get_attn_weights=False):
+        """Evaluation forward over one full window of codes (reference prior.py:312-349): returns (loss, metrics), or -
+        with get_attn_weights (True or a set of layer indices) - the recorded attention weights of those layers, which
+        is what lyric alignment reads (reference jukebox/align.py get_alignment).
+        No gradients are kept: optimisation is out of scope, the loss is the evaluation metric (bits per token)."""
+        assert isinstance(get_attn_weights, (bool, set))
+        tr = self.prior.transformer
+        if get_attn_weights:
+            tr.set_record_attn(get_attn_weights)
+        x_cond, y_cond, lyric = self.get_cond(z_conds, y)
+        if self.copy_input:
+            lyric = z[:, :self.n_tokens]
+        if self.single_enc_dec:
+            seq, x_cond = self.prior_preprocess([lyric, z], [None, x_cond])
+            (prime_loss, gen_loss), preds = self.prior(seq, x_cond, y_cond, fp16=fp16, get_sep_loss=True,
+                                                       get_preds=get_preds)
+        else:
+            enc = self.get_encoder_kv(lyric, fp16=fp16)
+            prime_loss = self.get_prime_loss(enc, lyric) if enc is not None else t.tensor(0.0, device=z.device)
+            gen_loss, preds = self.prior(z, x_cond, y_cond, enc, fp16=fp16, get_preds=get_preds)
+        if get_attn_weights:
+            ws = tr.ws
+            tr.set_record_attn(False)
+            return ws
+        total = self.total_loss_dims
+        loss = self.prime_loss_fraction * prime_loss * self.prime_loss_dims / total + gen_loss * self.gen_loss_dims / total
+        metrics = dict(bpd=gen_loss.clone(), prime_loss=prime_loss.clone(), gen_loss=gen_loss.clone())
+        if get_preds:
+            metrics["preds"] = preds.clone()
+        return loss, metrics
+
+    def forward(self, x, y=None, fp16=False, decode=False, get_preds=False):
+        """audio -> codes of every level -> z_forward at this level (reference prior.py:351-359)"""
+        z, *z_conds = self.encode(x, bs_chunks=x.shape[0])
+        loss, metrics = self.z_forward(z=z, z_conds=z_conds, y=y, fp16=fp16, get_preds=get_preds)
+        x_out = self.decode([z, *z_conds]) if decode else None
+        return x_out, loss, metrics

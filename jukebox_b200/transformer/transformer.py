@@ -84,12 +84,15 @@ class Transformer(nn.Module):
         self._engine = None
         self._engine_cfg = dict(bins=0, add_cond_after=True)
         self._enc_loaded = False
+        self._f32 = None
+        self._record_layers = []
         self.register_load_state_dict_post_hook(lambda m, keys: m.drop_engine())
 
     # ---- engine management --------------------------------------------------------------
     def drop_engine(self):
         self._engine = None
         self._enc_loaded = False
+        self._f32 = None
 
     def _apply(self, fn, *a, **k):          # .cuda() / .cpu() / .half(): packed weights are stale
         self.drop_engine()
@@ -130,22 +133,58 @@ class Transformer(nn.Module):
 
     # ---- reference surface --------------------------------------------------------------
     def set_record_attn(self, record_attn):
-        if record_attn:
-            raise NotImplementedError("record_attn needs the forward-mode attention path (SURVEY.md 8f row 1)")
-        self.ws = []
-        for l in self._attn_mods:
-            l.attn.record_attn = False
-            l.attn.w = None
+        """record_attn: False / True / a collection of layer indices (reference transformer.py:146-163).  Recorded
+        weights are produced by the forward-mode fp32 path and appear in `self.ws` after the next forward call, one
+        [n, heads, queries, keys] tensor per recorded layer, keys indexed by absolute position (for dense and enc-dec
+        layers - the ones alignment reads, prior.py:327-344 - that is the reference's own layout)."""
+        def _on(layer_idx):
+            if isinstance(record_attn, bool):
+                return record_attn
+            return layer_idx in record_attn
+        self._record_layers = [i for i in range(self.n_depth) if _on(i)]
+        for i, l in enumerate(self._attn_mods):
+            l.attn.record_attn = _on(i)
+        if not self._record_layers:
+            self.ws = []
+            for l in self._attn_mods:
+                l.attn.w = None
+
+    def f32_path(self):
+        from .f32 import F32Path
+        if self._f32 is None:
+            self._f32 = F32Path(self)
+        return self._f32
+
+    def _forward_f32(self, x, encoder_kv, sample):
+        path = self.f32_path()
+        n, l = x.shape[0], x.shape[1]
+        if sample:
+            p0 = path.pos
+            out, _ = path.run(x, encoder_kv, p0)
+            path.pos = p0 + l
+            for b in self._attn_mods:
+                b.attn._advance(n, l, False)
+            return out
+        assert l == self.n_ctx, f"forward mode runs whole sequences of n_ctx = {self.n_ctx} positions, got {l}"
+        path.reset()
+        out, ws = path.run(x, encoder_kv, 0, record=self._record_layers)
+        path.reset()
+        if self._record_layers:
+            for i in self._record_layers:      # prime layers keep music queries x lyric keys (factored_attention.py:103-105)
+                if self._attn_mods[i].attn_func == 7:
+                    ws[i] = ws[i][:, :, self.prime_len:, :self.prime_len]
+            self.ws = [ws[i] for i in self._record_layers]
+            for i in self._record_layers:
+                self._attn_mods[i].attn.w = ws[i]
+        return out
 
     def forward(self, x, encoder_kv=None, sample=False, fp16=False, fp16_out=False):
-        if not sample:
-            raise NotImplementedError(
-                "forward-mode (training / alignment) attention is the next hot-path row (SURVEY.md 8f.1); "
-                "sampling-mode prefill runs token by token through the decode engine")
-        if not fp16:
-            raise NotImplementedError("the decode engine implements the fp16 sampling path "
-                                      "(sampling_kwargs fp16=True, reference sample.py:239-241)")
         assert x.dim() == 3 and x.shape[2] == self.n_in
+        if not sample or not fp16:
+            # forward mode (any fp16 flag: computed in fp32, a superset of the reference's fp16 precision) and fp32
+            # sampling: csrc/f32_path.cu
+            out = self._forward_f32(x, encoder_kv, sample)
+            return out.half() if fp16_out else out
         n, l = x.shape[0], x.shape[1]
         eng = self.engine(n)
         has6 = any(b.attn_func == 6 for b in self._attn_mods)
@@ -169,7 +208,9 @@ class Transformer(nn.Module):
         for l in self._attn_mods:
             l.attn.check_cache(n_samples, sample_t, fp16)
         if self._engine is not None:
-            assert self._engine.position == sample_t, f"engine at {self._engine.position}, expected {sample_t}"
+            assert not fp16 or self._engine.position == sample_t, f"engine at {self._engine.position}, expected {sample_t}"
+        if not fp16 and self._f32 is not None:
+            assert self._f32.pos == sample_t, f"fp32 caches at {self._f32.pos}, expected {sample_t}"
 
     def del_cache(self):
         for l in self._attn_mods:
@@ -177,3 +218,5 @@ class Transformer(nn.Module):
         self._enc_loaded = False
         if self._engine is not None:
             self._engine.reset(0)
+        if self._f32 is not None:
+            self._f32.reset()

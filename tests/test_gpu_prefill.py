@@ -59,6 +59,8 @@ CASES = [
     (12, 256, 16, 2, 96, 8, 24, 61),    # given tokens run past the prime and past several blocks (ring layouts)
     (2, 256, 6, 1, 64, 4, None, 33),    # upsampler-like stack, one head
     (0, 256, 3, 4, 48, None, None, 17),  # dense
+    (2, 320, 6, 2, 64, 4, None, 33),    # K tail: n_state 80 is not a multiple of the 64-wide tcgen05 K block (5b: 1200, upsamplers: 480)
+    (2, 256, 6, 1, 1024, 8, None, 700),  # a long run of given tokens (continuation windows re-prime thousands)
 ]
 
 
@@ -123,3 +125,40 @@ def test_only_encode_forward_uses_prefill():
     e = rel_err(a.cpu().numpy(), b.cpu().numpy())
     print(f"only_encode prefill vs stepping: {e:.2e}")
     assert e < 5e-3
+
+
+def test_prefill_with_encoder_decoder_layers_and_get_preds(monkeypatch):
+    """enc-dec stacks (5b_lyrics: attn_func 6 layers read the lyric encoder's K/V) take the prefill path, and
+    primed_sample(get_preds=True) returns the given positions' logits from it: against stepping and the golden"""
+    from golden_util import Fixture
+    from jukebox_b200.prior.autoregressive import ConditionalAutoregressive2D
+    from oracle.synth import synth_state_dict
+    n_ctx, width, bins, enc = 64, 256, 64, 24
+    m = ConditionalAutoregressive2D((n_ctx,), bins, width=width, depth=8, heads=2, attn_order=6, blocks=4,
+                                    x_cond=True, y_cond=True, encoder_dims=enc)
+    sd = m.state_dict()
+    w = synth_state_dict([(k, tuple(v.shape)) for k, v in sd.items() if k != "x_out.weight"], 21)
+    w["x_out.weight"] = w["x_emb.weight"]
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    m = m.cuda().eval()
+    assert any(b.attn_func == 6 for b in m.transformer._attn_mods)
+    n, P = 3, 41
+    g = torch.Generator().manual_seed(9)
+    tokens = torch.randint(0, bins, (n, n_ctx), generator=g).cuda()
+    yc = torch.randn(n, 1, width, generator=g).cuda()
+    xc = (0.1 * torch.randn(n, n_ctx, width, generator=g)).cuda()
+    ekv = torch.randn(n, enc, width, generator=g).cuda()
+    eng = m._engine(n)
+    assert eng.prefill_capacity >= n_ctx - 1
+    outs = []
+    for cap in (None, 1):          # prefill in one pass / capacity 1 = every given token stepped
+        if cap is not None:
+            monkeypatch.setattr(type(eng), "prefill_capacity", property(lambda self: 1))
+        torch.manual_seed(0)
+        x, preds = m.primed_sample(n, tokens[:, :P].clone(), xc, yc, ekv, fp16=True, temp=0.05, get_preds=True,
+                                   sample_tokens=P + 6)
+        assert torch.equal(x[:, :P], tokens[:, :P])
+        outs.append((x.cpu(), preds.cpu().numpy()))
+    e = rel_err(outs[0][1], outs[1][1])
+    print(f"enc-dec prefill with get_preds vs stepping: logits {e:.2e}")
+    assert np.isfinite(outs[0][1]).all() and e < TOL

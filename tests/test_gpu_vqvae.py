@@ -110,8 +110,9 @@ def test_decode_is_batch_independent_and_linear_in_out_bias():
 
 @pytest.mark.parametrize("C,dil,T", [(64, 1, 1000), (64, 2187, 5000), (32, 27, 777), (32, 1, 64), (64, 9, 65)])
 def test_tensor_core_resblock_matches_exact_fma_kernel(C, dil, T):
-    """jk_resblock_tc (3xTF32 on mma.sync, decoder side) against jk_resblock_cl (exact fp32 FMAs): same block
-    (resnet.py:27-44), fp32-level agreement; ragged T, dilations beyond the tile, both channel counts"""
+    """jk_resblock_tc (split-precision tensor-core block, decoder side: fp16 x 3 on mma.sync.m16n8k16; the 3xTF32 kernel
+    with JK_RESBLOCK_TF32=1) against jk_resblock_cl (exact fp32 FMAs): same block (resnet.py:27-44), fp32-level
+    agreement; ragged T, dilations beyond the tile, both channel counts"""
     import ctypes as Cc
     from jukebox_b200._lib import lib, check, ptr, stream_ptr
     g = torch.Generator(device="cuda").manual_seed(C + dil)
@@ -129,5 +130,5 @@ def test_tensor_core_resblock_matches_exact_fma_kernel(C, dil, T):
             for k in range(3)) + b1.double()), w2[0].double()) + b2.double())
     e_exact = float((exact.double() - ref).abs().max() / ref.abs().max())
     e_tc = float((tc.double() - ref).abs().max() / ref.abs().max())
-    print(f"C {C} dil {dil} T {T}: exact-FMA kernel vs fp64 {e_exact:.1e}, 3xTF32 kernel vs fp64 {e_tc:.1e}")
+    print(f"C {C} dil {dil} T {T}: exact-FMA kernel vs fp64 {e_exact:.1e}, tensor-core kernel vs fp64 {e_tc:.1e}")
     assert e_exact < 2e-6 and e_tc < 4e-6

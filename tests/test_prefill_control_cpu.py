@@ -19,15 +19,17 @@ class FakeEngine:
     def set_encoder_kv(self, kv):
         self.calls.append(("enc", tuple(kv.shape)))
 
-    def prefill(self, n, P, **kw):
+    def prefill(self, n, P, h_out=None, **kw):
         assert self.position == 0
-        self.calls.append(("prefill", n, P))
+        self.calls.append(("prefill", n, P) if h_out is None else ("prefill", n, P, tuple(h_out.shape)))
+        if h_out is not None:
+            h_out.zero_()
         self.position = P
 
     def step(self, n, tokens=None, logits=None, **kw):
         self.calls.append(("step", self.position, logits is not None))
-        if logits is not None:
-            logits.zero_()
+        if logits is not None:       # [N, bins], or the whole [N, positions, bins] preds buffer (row = position)
+            (logits[:, self.position] if logits.dim() == 3 else logits).zero_()
         self.position += 1
 
 
@@ -56,8 +58,20 @@ def test_primed_sample_prefills_the_given_tokens_once(monkeypatch):
     assert torch.equal(z[:, :7], prime) and z.shape == (3, 12)
 
 
-def test_stepping_when_prefill_is_unavailable_or_preds_are_wanted(monkeypatch):
-    for capacity, get_preds in ((0, False), (4, False), (512, True)):
+def test_get_preds_takes_the_given_positions_logits_from_the_prefill(monkeypatch):
+    import jukebox_b200.transformer.f32 as f32
+    m, eng, drawn = _model(monkeypatch, capacity=512)
+    monkeypatch.setattr(f32, "linear_nk", lambda x, w: torch.full((x.shape[0], w.shape[0]), 7.0))
+    prime = torch.randint(0, 16, (2, 7))
+    z, preds = m.primed_sample(2, prime, fp16=True, get_preds=True, sample_tokens=10)
+    assert eng.calls[0] == ("prefill", 2, 7, (2, 7, 64))                 # activations of the given positions requested
+    assert [c[:2] for c in eng.calls[1:]] == [("step", 7), ("step", 8), ("step", 9)]
+    assert preds.shape == (2, 10, 16) and bool((preds[:, :7] == 7.0).all()) and bool((preds[:, 7:] == 0.0).all())
+    assert drawn == [7, 8, 9] and torch.equal(z[:, :7], prime)
+
+
+def test_stepping_when_prefill_is_unavailable(monkeypatch):
+    for capacity, get_preds in ((0, False), (4, False), (0, True)):
         m, eng, drawn = _model(monkeypatch, capacity)
         prime = torch.randint(0, 16, (2, 7))
         out = m.primed_sample(2, prime, fp16=True, get_preds=get_preds, sample_tokens=10)
