@@ -199,6 +199,9 @@ typedef struct jk_conv_args {
     int32_t relu_in;
     float scale;
     int32_t n;                        /* batch */
+    int32_t tensor_cores;             /* 0: exact fp32 FMAs in a fixed order (the encoder: its output feeds the bit-exact argmin);
+                                         1: decoder side - c_in, c_out in {32, 64} run on mma.sync with the fp16 x 3 split
+                                         (fp32-level accuracy, free summation order); other shapes ignore the flag */
 } jk_conv_args;
 int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream);
 

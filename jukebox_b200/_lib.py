@@ -67,7 +67,7 @@ class ConvArgs(C.Structure):
                 ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p),
                 ("n_taps", C.c_int32), ("tap_off", C.c_int32 * 4), ("in_stride", C.c_int32),
                 ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("relu_in", C.c_int32),
-                ("scale", C.c_float), ("n", C.c_int32)]
+                ("scale", C.c_float), ("n", C.c_int32), ("tensor_cores", C.c_int32)]
 
 
 # every symbol include/jkb200.h declares: name -> (restype, argtypes)

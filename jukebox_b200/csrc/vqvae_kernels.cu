@@ -598,8 +598,8 @@ int launch_resblock_tc(const float* x, float* out, const float* w1, const float*
 // (cvt.satfinite); VQ-VAE activations are O(1).  Small activations lose nothing that matters: an fp16 remainder below
 // 2^-14 is kept to an ABSOLUTE 2^-25.
 //   * ONE WARP PER 16-POSITION TILE: a warp's output rows need only its own rows of the three tap tiles and of the hidden
-//     tile, so nothing is shared between warps except the weights - no CTA barrier in the tile loop, and the eight warps of
-//     a CTA drift apart so that one's global loads overlap another's MMAs
+//     tile, so nothing is shared between warps except the weights - no CTA barrier in the tile loop, and the sixteen warps
+//     of a CTA (4 per scheduler) drift apart so that one's global loads overlap another's MMAs
 //   * persistent CTAs (grid = #SMs), W1 / W2 hi + lo planes staged once per CTA
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
@@ -609,6 +609,13 @@ __device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
     const float r = x - __half2float(hi);
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(r));
     lo = __ushort_as_half(l);
+}
+// two values at once: hi / lo as packed half2 (a in the low half), 6 instructions for the pair
+__device__ __forceinline__ void split_h2x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    float ha, hb;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(ha), "=f"(hb) : "r"(hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -631,9 +638,9 @@ constexpr float kWScale = 256.f, kWInv = 1.f / 256.f;
 template <int C>
 struct ResH2 {
     static constexpr int XS = C + 8;                       // halfs per row: 16-byte aligned rows an odd number of 16-byte units apart
-    static constexpr int NT = C / 8, WARPS = 8;
+    static constexpr int NT = C / 8, WARPS = 16;
     static constexpr int w_halfs = 2 * (3 * C + C) * XS;   // W1 hi, W1 lo, W2 hi, W2 lo
-    static constexpr int warp_halfs = 2 * 3 * 16 * XS;     // a warp's tap tiles, hi and lo; the hidden tile reuses tap 0
+    static constexpr int warp_halfs = 2 * 16 * XS;         // ONE tap tile of a warp (hi, lo); the hidden tile reuses it
     static constexpr size_t smem = (size_t)(w_halfs + WARPS * warp_halfs) * 2;
 };
 
@@ -660,84 +667,87 @@ __device__ __forceinline__ void h2_kstep(float (&acc)[C / 8][4], const __half* a
     }
 }
 
+// 16 warps per CTA (4 per scheduler; <= 128 registers each): a warp stages ONE tap tile at a time - the global loads of the
+// next tap (or of the next tile's first tap) are in flight while the current tap's MMAs issue
 template <int C>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 resblock_h2_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ w1,
                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                    long long T, int dil, float rs, long long tiles_per_clip, long long total_tiles) {
-    constexpr int XS = ResH2<C>::XS, NT = ResH2<C>::NT;
+    constexpr int XS = ResH2<C>::XS, NT = ResH2<C>::NT, WARPS = ResH2<C>::WARPS;
     extern __shared__ __align__(16) __half hsm[];
     __half* w1h = hsm;                          // [3 C][XS]
     __half* w1l = w1h + 3 * C * XS;
     __half* w2h = w1l + 3 * C * XS;             // [C][XS]
     __half* w2l = w2h + C * XS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __half* xh = w2l + C * XS + warp * ResH2<C>::warp_halfs;      // [3][16][XS] relu(x) at t + (tap - 1) * dil
-    __half* xl = xh + 3 * 16 * XS;
+    __half* xh = w2l + C * XS + warp * ResH2<C>::warp_halfs;      // [16][XS] relu(x) at t + (tap - 1) * dil, then the hidden tile
+    __half* xl = xh + 16 * XS;
     const int g = lane >> 2, t4 = lane & 3;
-    for (int i = tid; i < 3 * C * C; i += 256) {
+    for (int i = tid; i < 3 * C * C; i += WARPS * 32) {
         const int o = (i / C) * XS + i % C;
         split_h2(kWScale * __ldg(w1 + i), w1h[o], w1l[o]);
     }
-    for (int i = tid; i < C * C; i += 256) {
+    for (int i = tid; i < C * C; i += WARPS * 32) {
         const int o = (i / C) * XS + i % C;
         split_h2(kWScale * __ldg(w2 + i), w2h[o], w2l[o]);
     }
     __syncthreads();
-    constexpr int TX = C / 4, PER = 16 * TX / 32;         // float4 loads per lane per tap tile
+    constexpr int TX = C / 4, PER = 16 * TX / 32, RJ = 32 / TX;   // float4 loads per lane per tap tile; rows between them
+    const int lr = lane / TX, lc = lane % TX;             // this lane's row (+ j * RJ) and 16-byte chunk of a tap tile
+    const long long stride = (long long)gridDim.x * WARPS;
+    float4 v[PER];
+    auto issue = [&](long long tile, int tap) {           // tap tile rows -> registers (zeros outside the clip)
+        if (tile >= total_tiles) return;
+        const long long nb = tile / tiles_per_clip;
+        const long long tb = (tile - nb * tiles_per_clip) * 16 + (long long)(tap - 1) * dil + lr;
+        const float4* p = reinterpret_cast<const float4*>(x + ((size_t)nb * T + tb) * C) + lc;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const long long tp = tb + j * RJ;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp >= 0 && tp < T) v[j] = __ldg(p + j * RJ * TX);
+        }
+    };
+    long long tile = (long long)blockIdx.x * WARPS + warp;
+    issue(tile, 0);
 #pragma unroll 1
-    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < total_tiles; tile += (long long)gridDim.x * 8) {
+    for (; tile < total_tiles; tile += stride) {
         const long long nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * 16;
         const float* xin = x + (size_t)nb * T * C;
         float* xout = out + (size_t)nb * T * C;
-        __syncwarp();                           // the previous tile's fragment reads are done
-#pragma unroll
-        for (int tap = 0; tap < 3; ++tap) {
-            const long long off = (long long)(tap - 1) * dil;
-            float4 v[PER];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int i = lane + 32 * j, tt = i / TX, c4 = i % TX;
-                const long long tp = t0 + tt + off;
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tp >= 0 && tp < T) v[j] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)tp * C) + c4);
-            }
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int i = lane + 32 * j, tt = i / TX, c4 = i % TX;
-                __half h[4], l[4];
-                split_h2(fmaxf(v[j].x, 0.f), h[0], l[0]);
-                split_h2(fmaxf(v[j].y, 0.f), h[1], l[1]);
-                split_h2(fmaxf(v[j].z, 0.f), h[2], l[2]);
-                split_h2(fmaxf(v[j].w, 0.f), h[3], l[3]);
-                *reinterpret_cast<uint2*>(xh + (tap * 16 + tt) * XS + c4 * 4) = *reinterpret_cast<const uint2*>(h);
-                *reinterpret_cast<uint2*>(xl + (tap * 16 + tt) * XS + c4 * 4) = *reinterpret_cast<const uint2*>(l);
-            }
-        }
-        __syncwarp();
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-        for (int tap = 0; tap < 3; ++tap)
+        for (int tap = 0; tap < 3; ++tap) {
+            __syncwarp();                       // the previous fragment reads of this buffer are done
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                uint2 h, l;
+                split_h2x2(fmaxf(v[j].x, 0.f), fmaxf(v[j].y, 0.f), h.x, l.x);
+                split_h2x2(fmaxf(v[j].z, 0.f), fmaxf(v[j].w, 0.f), h.y, l.y);
+                *reinterpret_cast<uint2*>(xh + (lr + j * RJ) * XS + lc * 4) = h;
+                *reinterpret_cast<uint2*>(xl + (lr + j * RJ) * XS + lc * 4) = l;
+            }
+            if (tap < 2) issue(tile, tap + 1); else issue(tile + stride, 0);      // in flight during the MMAs below
+            __syncwarp();
 #pragma unroll
             for (int k16 = 0; k16 < C / 16; ++k16)
-                h2_kstep<C>(acc, xh + tap * 16 * XS + k16 * 16, xl + tap * 16 * XS + k16 * 16,
-                            w1h + (tap * C + k16 * 16) * XS, w1l + (tap * C + k16 * 16) * XS, lane);
-        __syncwarp();                           // tap tile 0 is dead: the hidden tile takes its place
+                h2_kstep<C>(acc, xh + k16 * 16, xl + k16 * 16, w1h + (tap * C + k16 * 16) * XS, w1l + (tap * C + k16 * 16) * XS, lane);
+        }
+        __syncwarp();                           // the tap tile is dead: the hidden tile takes its place
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {       // hidden = relu(conv1 + b1), split, -> shared memory (this warp's rows only)
             const int col = nt * 8 + 2 * t4;
             const float2 bv = __ldg(reinterpret_cast<const float2*>(b1 + col));
-            __half h[2], l[2];
-            split_h2(fmaxf(fmaf(acc[nt][0], kWInv, bv.x), 0.f), h[0], l[0]);
-            split_h2(fmaxf(fmaf(acc[nt][1], kWInv, bv.y), 0.f), h[1], l[1]);
-            *reinterpret_cast<uint32_t*>(xh + g * XS + col) = *reinterpret_cast<const uint32_t*>(h);
-            *reinterpret_cast<uint32_t*>(xl + g * XS + col) = *reinterpret_cast<const uint32_t*>(l);
-            split_h2(fmaxf(fmaf(acc[nt][2], kWInv, bv.x), 0.f), h[0], l[0]);
-            split_h2(fmaxf(fmaf(acc[nt][3], kWInv, bv.y), 0.f), h[1], l[1]);
-            *reinterpret_cast<uint32_t*>(xh + (g + 8) * XS + col) = *reinterpret_cast<const uint32_t*>(h);
-            *reinterpret_cast<uint32_t*>(xl + (g + 8) * XS + col) = *reinterpret_cast<const uint32_t*>(l);
+            uint32_t h, l;
+            split_h2x2(fmaxf(fmaf(acc[nt][0], kWInv, bv.x), 0.f), fmaxf(fmaf(acc[nt][1], kWInv, bv.y), 0.f), h, l);
+            *reinterpret_cast<uint32_t*>(xh + g * XS + col) = h;
+            *reinterpret_cast<uint32_t*>(xl + g * XS + col) = l;
+            split_h2x2(fmaxf(fmaf(acc[nt][2], kWInv, bv.x), 0.f), fmaxf(fmaf(acc[nt][3], kWInv, bv.y), 0.f), h, l);
+            *reinterpret_cast<uint32_t*>(xh + (g + 8) * XS + col) = h;
+            *reinterpret_cast<uint32_t*>(xl + (g + 8) * XS + col) = l;
             acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
         }
         __syncwarp();
@@ -753,10 +763,10 @@ resblock_h2_kernel(const float* __restrict__ x, float* __restrict__ out, const f
                 const long long t = t0 + g + 8 * hlf;
                 if (t < T) {
                     const float2 r = __ldg(reinterpret_cast<const float2*>(xin + (size_t)t * C + col));
-                    float2 v;
-                    v.x = rs * fmaf(acc[nt][2 * hlf], kWInv, bv.x); v.x += r.x;
-                    v.y = rs * fmaf(acc[nt][2 * hlf + 1], kWInv, bv.y); v.y += r.y;
-                    *reinterpret_cast<float2*>(xout + (size_t)t * C + col) = v;
+                    float2 o;
+                    o.x = rs * fmaf(acc[nt][2 * hlf], kWInv, bv.x); o.x += r.x;
+                    o.y = rs * fmaf(acc[nt][2 * hlf + 1], kWInv, bv.y); o.y += r.y;
+                    *reinterpret_cast<float2*>(xout + (size_t)t * C + col) = o;
                 }
             }
         }
@@ -777,8 +787,147 @@ int launch_resblock_h2(const float* x, float* out, const float* w1, const float*
         attr_set[dev & 63] = true;
     }
     const long long per_clip = (T + 15) / 16, total = per_clip * n;
-    const unsigned grid = (unsigned)std::min<long long>((total + 7) / 8, sms[dev & 63]);
-    resblock_h2_kernel<C><<<grid, 256, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs, per_clip, total);
+    constexpr int WARPS = ResH2<C>::WARPS;
+    const unsigned grid = (unsigned)std::min<long long>((total + WARPS - 1) / WARPS, sms[dev & 63]);
+    resblock_h2_kernel<C><<<grid, WARPS * 32, smem, stream>>>(x, out, w1, b1, w2, b2, T, dil, rs, per_clip, total);
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Tap-GEMM convolution with the same fp16 x 3 split, for the decoder-side convs BETWEEN the residual blocks (the k3 input
+// conv of a DecoderConvBock, the two phases of its k4-s2 transposed convs, Decoder.out's wide cousins; encdec.py:28-46):
+// out[t*os + oo, :] = res + scale * (sum_j x[t*is + off_j, :] . W_j + b), c_in, c_out in {32, 64}.
+// One warp per 16 output positions like resblock_h2_kernel; weights (<= 4 taps) staged once per persistent CTA.
+// ---------------------------------------------------------------------------------------
+template <int CI, int CO>
+struct ConvH2 {
+    static constexpr int XA = CI + 8, XB = CO + 8, NT = CO / 8, WARPS = 16;
+    static constexpr int w_halfs = 2 * 4 * CI * XB;
+    static constexpr int warp_halfs = 2 * 16 * XA;         // one tap tile of a warp, hi and lo
+    static constexpr size_t smem = (size_t)(w_halfs + WARPS * warp_halfs) * 2;
+};
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(512, 1) conv1d_h2_kernel(ConvP P, long long tiles_per_clip, long long total_tiles) {
+    constexpr int XA = ConvH2<CI, CO>::XA, XB = ConvH2<CI, CO>::XB, NT = ConvH2<CI, CO>::NT, WARPS = ConvH2<CI, CO>::WARPS;
+    extern __shared__ __align__(16) __half hsm[];
+    const int ntap = P.n_taps;
+    __half* wh = hsm;                           // [ntap * CI][XB]
+    __half* wl = wh + 4 * CI * XB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __half* xh = wl + 4 * CI * XB + warp * ConvH2<CI, CO>::warp_halfs;       // [16][XA]: the current tap's rows
+    __half* xl = xh + 16 * XA;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int i = tid; i < ntap * CI * CO; i += WARPS * 32) {
+        const int o = (i / CO) * XB + i % CO;
+        split_h2(kWScale * __ldg(P.w + i), wh[o], wl[o]);
+    }
+    __syncthreads();
+    constexpr int TX = CI / 4, PER = 16 * TX / 32, RJ = 32 / TX;
+    const int lr = lane / TX, lc = lane % TX;
+    const long long rows_out = P.t_out * P.out_stride;
+    const int r = lane & 15, c8 = (lane >> 4) * 8;
+    const long long stride = (long long)gridDim.x * WARPS;
+    float4 v[PER];
+    auto issue = [&](long long tile, int tap) {
+        if (tile >= total_tiles) return;
+        const long long nb = tile / tiles_per_clip, to = (tile - nb * tiles_per_clip) * 16 + lr;      // output row of j = 0
+        const long long off = tap == 0 ? P.tap_off[0] : tap == 1 ? P.tap_off[1] : tap == 2 ? P.tap_off[2] : P.tap_off[3];
+        const long long tb = to * P.in_stride + off;
+        const float4* p = reinterpret_cast<const float4*>(P.in + ((size_t)nb * P.t_in + tb) * CI) + lc;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const long long tp = tb + (long long)j * RJ * P.in_stride;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp >= 0 && tp < P.t_in && to + j * RJ < P.t_out) v[j] = __ldg(p + (size_t)j * RJ * P.in_stride * TX);
+        }
+    };
+    long long tile = (long long)blockIdx.x * WARPS + warp;
+    issue(tile, 0);
+#pragma unroll 1
+    for (; tile < total_tiles; tile += stride) {
+        const long long nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * 16;
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 1
+        for (int tap = 0; tap < ntap; ++tap) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                if (P.relu_in) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+                uint2 h, l;
+                split_h2x2(v[j].x, v[j].y, h.x, l.x);
+                split_h2x2(v[j].z, v[j].w, h.y, l.y);
+                *reinterpret_cast<uint2*>(xh + (lr + j * RJ) * XA + lc * 4) = h;
+                *reinterpret_cast<uint2*>(xl + (lr + j * RJ) * XA + lc * 4) = l;
+            }
+            if (tap + 1 < ntap) issue(tile, tap + 1); else issue(tile + stride, 0);
+            __syncwarp();
+#pragma unroll
+            for (int k16 = 0; k16 < CI / 16; ++k16) {
+                uint32_t fh[4], fl[4];
+                ldsm_x4(fh, xh + r * XA + k16 * 16 + c8);
+                ldsm_x4(fl, xl + r * XA + k16 * 16 + c8);
+                const __half* bh = wh + (tap * CI + k16 * 16 + r) * XB + c8;
+                const __half* bl = wl + (tap * CI + k16 * 16 + r) * XB + c8;
+#pragma unroll
+                for (int np = 0; np < CO / 16; ++np) {
+                    uint32_t qh[4], ql[4];
+                    ldsm_x4_t(qh, bh + np * 16);
+                    ldsm_x4_t(ql, bl + np * 16);
+                    mma_h(acc[2 * np], fl, qh[0], qh[1]);
+                    mma_h(acc[2 * np], fh, ql[0], ql[1]);
+                    mma_h(acc[2 * np], fh, qh[0], qh[1]);
+                    mma_h(acc[2 * np + 1], fl, qh[2], qh[3]);
+                    mma_h(acc[2 * np + 1], fh, ql[2], ql[3]);
+                    mma_h(acc[2 * np + 1], fh, qh[2], qh[3]);
+                }
+            }
+        }
+        float* out = P.out + (size_t)nb * rows_out * CO;
+        const float* res = P.res ? P.res + (size_t)nb * rows_out * CO : nullptr;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = nt * 8 + 2 * t4;
+            float2 bv = make_float2(0.f, 0.f);
+            if (P.bias) bv = __ldg(reinterpret_cast<const float2*>(P.bias + col));
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const long long t = t0 + g + 8 * hlf;
+                if (t < P.t_out) {
+                    const long long orow = t * P.out_stride + P.out_offset;
+                    float2 o;
+                    o.x = P.scale * fmaf(acc[nt][2 * hlf], kWInv, bv.x);
+                    o.y = P.scale * fmaf(acc[nt][2 * hlf + 1], kWInv, bv.y);
+                    if (res) {
+                        const float2 rr = __ldg(reinterpret_cast<const float2*>(res + (size_t)orow * CO + col));
+                        o.x += rr.x; o.y += rr.y;
+                    }
+                    *reinterpret_cast<float2*>(out + (size_t)orow * CO + col) = o;
+                }
+            }
+        }
+    }
+}
+
+template <int CI, int CO>
+int launch_conv_h2(const ConvP& P, int n, cudaStream_t stream) {
+    constexpr size_t smem = ConvH2<CI, CO>::smem;
+    static bool attr_set[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        JK_CHECK_CUDA(cudaFuncSetAttribute(conv1d_h2_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JK_CHECK_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+        attr_set[dev & 63] = true;
+    }
+    const long long per_clip = (P.t_out + 15) / 16, total = per_clip * n;
+    constexpr int WARPS = ConvH2<CI, CO>::WARPS;
+    const unsigned grid = (unsigned)std::min<long long>((total + WARPS - 1) / WARPS, sms[dev & 63]);
+    conv1d_h2_kernel<CI, CO><<<grid, WARPS * 32, smem, stream>>>(P, per_clip, total);
     JK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -786,37 +935,57 @@ int launch_resblock_h2(const float* x, float* out, const float* w1, const float*
 // c_out <= 4 (the decoder's final Conv1d(emb_width -> 1 audio channel, k3), encdec.py:109): one thread per output
 // position, weights in shared memory.  The 64 x 64 tile kernel would spend 63/64 of its FMAs on padding here;
 // this one is a stream over the input (HBM bound).  Same accumulation order as the tile kernel (tap, then channel).
-__global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P) {
-    extern __shared__ float wsm[];                       // [n_taps][c_in][c_out]
-    const int nw = P.n_taps * P.c_in * P.c_out;
+__global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P, int span, int min_off) {
+    extern __shared__ __align__(16) float wsm[];         // [n_taps][c_in][c_out] | input rows [256 + span][c_in + 4]
+    const int CI = P.c_in, CO = P.c_out, XS = CI + 4;
+    const int nw = P.n_taps * CI * CO;
+    float* xs = wsm + ((nw + 3) & ~3);
     for (int i = threadIdx.x; i < nw; i += 256) wsm[i] = P.w[i];
-    __syncthreads();
-    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (t >= P.t_out) return;
+    const long long t0 = (long long)blockIdx.x * 256, t = t0 + threadIdx.x;
     const int nb = blockIdx.y;
-    const float* in = P.in + (size_t)nb * P.t_in * P.c_in;
+    const float* in = P.in + (size_t)nb * P.t_in * CI;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int tap = 0; tap < P.n_taps; ++tap) {
-        const long long tp = t * P.in_stride + P.tap_off[tap];
-        if (tp < 0 || tp >= P.t_in) continue;            // zero padding: fmaf(0, w, acc) == acc
-        const float* xr = in + (size_t)tp * P.c_in;
-        const float* wr = wsm + (size_t)tap * P.c_in * P.c_out;
-        for (int c = 0; c < P.c_in; c += 4) {
-            float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const int c4n = CI >> 2;
+    // Input rows are loaded by the whole CTA with consecutive lanes on consecutive 16-byte chunks (one thread per output row
+    // would touch 32 different rows per instruction), zero outside [0, t_in).  span >= 0: the taps of all 256 outputs lie in
+    // one window of 256 + span rows (stride 1, small dilation: the decoder's output conv) - staged ONCE; else tap by tap.
+    const int passes = span >= 0 ? 1 : P.n_taps;
+    for (int pass = 0; pass < passes; ++pass) {
+        __syncthreads();
+        const long long off = span >= 0 ? min_off : (pass == 0 ? P.tap_off[0] : pass == 1 ? P.tap_off[1] : pass == 2 ? P.tap_off[2] : P.tap_off[3]);
+        const int rows = span >= 0 ? 256 + span : 256;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < rows * c4n; i += 256) {
+            const int r = i / c4n, c4 = i - r * c4n;
+            const long long tp = span >= 0 ? t0 + r + off : (t0 + r) * P.in_stride + off;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp >= 0 && tp < P.t_in) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)tp * CI) + c4);
             if (P.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            const float xv[4] = {v.x, v.y, v.z, v.w};
+            *reinterpret_cast<float4*>(xs + (size_t)r * XS + c4 * 4) = v;
+        }
+        __syncthreads();
+        const int tap_lo = span >= 0 ? 0 : pass, tap_hi = span >= 0 ? P.n_taps : pass + 1;
+        for (int tap = tap_lo; tap < tap_hi; ++tap) {
+            const int toff = tap == 0 ? P.tap_off[0] : tap == 1 ? P.tap_off[1] : tap == 2 ? P.tap_off[2] : P.tap_off[3];
+            const float* xr = xs + (size_t)(threadIdx.x + (span >= 0 ? toff - min_off : 0)) * XS;
+            const float* wr = wsm + (size_t)tap * CI * CO;
+            for (int c = 0; c < CI; c += 4) {            // same accumulation order as the tile kernel: tap, then channel
+                const float4 v = *reinterpret_cast<const float4*>(xr + c);
+                const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 4; ++e)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < P.c_out) acc[j] = fmaf(xv[e], wr[(c + e) * P.c_out + j], acc[j]);
+                    for (int j = 0; j < 4; ++j)
+                        if (j < CO) acc[j] = fmaf(xv[e], wr[(c + e) * CO + j], acc[j]);
+            }
         }
     }
+    if (t >= P.t_out) return;
     const long long rows_out = P.t_out * P.out_stride;
     const long long orow = t * P.out_stride + P.out_offset;
-    float* out = P.out + ((size_t)nb * rows_out + orow) * P.c_out;
-    const float* res = P.res ? P.res + ((size_t)nb * rows_out + orow) * P.c_out : nullptr;
-    for (int j = 0; j < P.c_out; ++j) {
+    float* out = P.out + ((size_t)nb * rows_out + orow) * CO;
+    const float* res = P.res ? P.res + ((size_t)nb * rows_out + orow) * CO : nullptr;
+    for (int j = 0; j < CO; ++j) {
         float v = P.scale * (acc[j] + (P.bias ? P.bias[j] : 0.f));
         if (res) v += res[j];
         out[j] = v;
@@ -915,11 +1084,32 @@ extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
     for (int i = 0; i < 4; ++i) P.tap_off[i] = a->tap_off[i];
     P.in_stride = a->in_stride; P.out_stride = a->out_stride; P.out_offset = a->out_offset; P.relu_in = a->relu_in;
     P.scale = a->scale;
-    if (a->c_out <= 4 && a->c_in % 4 == 0 && (size_t)a->n_taps * a->c_in * a->c_out * 4 <= 32768) {
+    if (a->c_out <= 4 && a->c_in % 4 == 0 && a->c_in <= 128 && ((uintptr_t)a->in & 15) == 0 &&
+        (size_t)a->n_taps * a->c_in * a->c_out * 4 <= 32768) {
         dim3 g((unsigned)((a->t_out + 255) / 256), (unsigned)a->n);
-        conv1d_cl_narrow_kernel<<<g, 256, (size_t)a->n_taps * a->c_in * a->c_out * 4, stream>>>(P);
+        int lo = a->tap_off[0], hi = a->tap_off[0];
+        for (int i = 1; i < a->n_taps; ++i) { lo = std::min(lo, (int)a->tap_off[i]); hi = std::max(hi, (int)a->tap_off[i]); }
+        const int span = (a->in_stride == 1 && hi - lo <= 16) ? hi - lo : -1;        // one staging window covers every tap
+        const size_t nsm = (((size_t)a->n_taps * a->c_in * a->c_out + 3) & ~(size_t)3) * 4 +
+                           (size_t)(256 + std::max(span, 0)) * (a->c_in + 4) * 4;
+        static bool narrow_attr[64] = {};
+        int dev = 0;
+        JK_CHECK_CUDA(cudaGetDevice(&dev));
+        if (!narrow_attr[dev & 63]) {
+            JK_CHECK_CUDA(cudaFuncSetAttribute(conv1d_cl_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            narrow_attr[dev & 63] = true;
+        }
+        conv1d_cl_narrow_kernel<<<g, 256, nsm, stream>>>(P, span, lo);
         JK_CHECK_CUDA(cudaGetLastError());
         return 0;
+    }
+    static const bool conv_exact = getenv("JK_CONV_EXACT") != nullptr;      // A/B: keep the FMA tile kernel for flagged convs
+    if (a->tensor_cores && !conv_exact && (a->c_in == 32 || a->c_in == 64) && (a->c_out == 32 || a->c_out == 64) &&
+        (((uintptr_t)a->in | (uintptr_t)a->out | (uintptr_t)a->bias | (uintptr_t)a->res) & 15) == 0) {
+        if (a->c_in == 64 && a->c_out == 64) return launch_conv_h2<64, 64>(P, a->n, stream);
+        if (a->c_in == 64 && a->c_out == 32) return launch_conv_h2<64, 32>(P, a->n, stream);
+        if (a->c_in == 32 && a->c_out == 64) return launch_conv_h2<32, 64>(P, a->n, stream);
+        return launch_conv_h2<32, 32>(P, a->n, stream);
     }
     if ((a->c_out == 64 || a->c_out == 32) && a->c_in % 4 == 0 && a->c_in >= 4 && a->c_in <= 64 &&
         (((uintptr_t)a->in | (uintptr_t)a->out | (uintptr_t)a->w | (uintptr_t)a->bias | (uintptr_t)a->res) & 15) == 0 &&
@@ -945,6 +1135,7 @@ extern "C" int jk_resblock_cl(const float* x, float* out, float* tmp, const floa
     }
     JK_REQUIRE(tmp, "tmp ([n, T, Cs] floats) is required for shapes without the fused kernel");
     jk_conv_args a;
+    a.tensor_cores = 0;
     a.in = x; a.t_in = T; a.c_in = C; a.out = tmp; a.t_out = T; a.c_out = Cs; a.w = w1; a.bias = b1; a.res = nullptr;
     a.n_taps = 3; a.tap_off[0] = -dilation; a.tap_off[1] = 0; a.tap_off[2] = dilation; a.tap_off[3] = 0;
     a.in_stride = 1; a.out_stride = 1; a.out_offset = 0; a.relu_in = 1; a.scale = 1.0f; a.n = n;

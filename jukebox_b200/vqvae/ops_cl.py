@@ -12,7 +12,7 @@ from .._lib import lib, check, ptr, stream_ptr
 
 
 def _conv(x, w_packed, bias, t_out, c_out, taps, in_stride=1, out=None, out_stride=1, out_offset=0,
-          relu_in=False, scale=1.0, res=None):
+          relu_in=False, scale=1.0, res=None, tensor_cores=False):
     assert x.dim() == 3 and x.dtype == t.float32
     x = x.contiguous()
     n, t_in, c_in = x.shape
@@ -27,6 +27,7 @@ def _conv(x, w_packed, bias, t_out, c_out, taps, in_stride=1, out=None, out_stri
         a.tap_off[i] = int(o)
     a.in_stride, a.out_stride, a.out_offset = in_stride, out_stride, out_offset
     a.relu_in, a.scale, a.n = int(relu_in), float(scale), n
+    a.tensor_cores = int(bool(tensor_cores))
     check(lib().jk_conv1d_cl(C.byref(a), stream_ptr()))
     return out
 
@@ -37,6 +38,9 @@ class _ConvBase(nn.Module):
     def __init__(self):
         super().__init__()
         self._packed = None
+        # decoder-side stacks set this (resnet.use_tensor_cores): split-precision tensor-core kernel, free summation order.
+        # The encoder, whose output feeds the bit-exact codebook argmin, keeps the exact-FMA kernels.
+        self.tensor_cores = False
         self.register_load_state_dict_post_hook(lambda m, keys: m._drop())
 
     def _drop(self):
@@ -84,7 +88,7 @@ class Conv1d(_ConvBase):
         w, b = self.packed()
         t_out = x.shape[1] // self.stride
         return _conv(x, w, b, t_out, self.n_out, self.taps, in_stride=self.stride, relu_in=relu_in,
-                     scale=scale, res=res)
+                     scale=scale, res=res, tensor_cores=self.tensor_cores)
 
 
 class ConvTranspose1d(_ConvBase):
@@ -113,8 +117,8 @@ class ConvTranspose1d(_ConvBase):
             self._phases = (t.stack([w[1], w[3]]).contiguous(), t.stack([w[0], w[2]]).contiguous())
         n, T, _ = x.shape
         out = t.empty(n, 2 * T, self.n_out, dtype=t.float32, device=x.device)
-        _conv(x, self._phases[0], b, T, self.n_out, [0, -1], out=out, out_stride=2, out_offset=0)
-        _conv(x, self._phases[1], b, T, self.n_out, [1, 0], out=out, out_stride=2, out_offset=1)
+        _conv(x, self._phases[0], b, T, self.n_out, [0, -1], out=out, out_stride=2, out_offset=0, tensor_cores=self.tensor_cores)
+        _conv(x, self._phases[1], b, T, self.n_out, [1, 0], out=out, out_stride=2, out_offset=1, tensor_cores=self.tensor_cores)
         return out
 
 

@@ -68,8 +68,9 @@ class Resnet1D(nn.Module):
 
 
 def use_tensor_cores(module, on=True):
-    """switch every ResConv1DBlock below `module` to the 3xTF32 tensor-core kernel (decoder-side stacks only)"""
+    """switch every ResConv1DBlock and channels-last conv below `module` to the split-precision tensor-core kernels
+    (jk_resblock_tc, jk_conv1d_cl with tensor_cores = 1) - decoder-side stacks only"""
     for m in module.modules():
-        if isinstance(m, ResConv1DBlock):
+        if hasattr(m, "tensor_cores"):
             m.tensor_cores = bool(on)
     return module

@@ -132,3 +132,41 @@ def test_tensor_core_resblock_matches_exact_fma_kernel(C, dil, T):
     e_tc = float((tc.double() - ref).abs().max() / ref.abs().max())
     print(f"C {C} dil {dil} T {T}: exact-FMA kernel vs fp64 {e_exact:.1e}, tensor-core kernel vs fp64 {e_tc:.1e}")
     assert e_exact < 2e-6 and e_tc < 4e-6
+
+
+@pytest.mark.parametrize("kind,ci,co,T", [("k3", 64, 64, 1000), ("k3", 64, 32, 333), ("k3d", 32, 32, 5000), ("up", 64, 64, 777),
+                                          ("up", 32, 64, 64), ("down", 32, 64, 1024)])
+def test_tensor_core_conv_matches_exact_kernel(kind, ci, co, T):
+    """decoder-side convs with tensor_cores set (fp16 x 3 split on mma.sync) against the exact-FMA kernels and torch:
+    k3 'same' (dilated too), the two phases of the k4-s2 transposed conv, the strided k4 conv; ragged T"""
+    from jukebox_b200.vqvae.ops_cl import Conv1d, ConvTranspose1d
+    torch.manual_seed(ci + co + T)
+    if kind == "up":
+        m = ConvTranspose1d(ci, co, 4, 2, 1)
+    elif kind == "down":
+        m = Conv1d(ci, co, 4, 2, 1)
+    else:
+        d = 27 if kind == "k3d" else 1
+        m = Conv1d(ci, co, 3, 1, d, d)
+    m = m.cuda()
+    x = torch.randn(3, T, ci, device="cuda")
+    with torch.no_grad():
+        exact = m(x)
+        m.tensor_cores = True
+        tc = m(x)
+    # fp64 reference through torch on the same weights
+    with torch.no_grad():
+        md = {k: v.double() for k, v in m.state_dict().items()}
+        xd = x.double().transpose(1, 2)
+        if kind == "up":
+            ref = torch.nn.functional.conv_transpose1d(xd, md["weight"], md["bias"], stride=2, padding=1)
+        elif kind == "down":
+            ref = torch.nn.functional.conv1d(xd, md["weight"], md["bias"], stride=2, padding=1)
+        else:
+            ref = torch.nn.functional.conv1d(xd, md["weight"], md["bias"], padding=d, dilation=d)
+        ref = ref.transpose(1, 2)
+    assert tc.shape == exact.shape == ref.shape
+    e_exact = float((exact.double() - ref).abs().max() / ref.abs().max())
+    e_tc = float((tc.double() - ref).abs().max() / ref.abs().max())
+    print(f"{kind} {ci}->{co} T {T}: exact kernel vs fp64 {e_exact:.1e}, tensor-core kernel vs fp64 {e_tc:.1e}")
+    assert e_exact < 2e-6 and e_tc < 4e-6
