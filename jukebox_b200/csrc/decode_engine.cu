@@ -46,6 +46,23 @@
 
 using namespace jk;
 
+// build-time variants (A/B runs: tools/build_variants.sh); the defaults are the measured winners
+#ifndef JK_MMA_ALL_WARPS
+#define JK_MMA_ALL_WARPS 1
+#endif
+#ifndef JK_QKV_POLL_BATCH
+#define JK_QKV_POLL_BATCH 1
+#endif
+#ifndef JK_SKIP_FOREIGN_WAIT
+#define JK_SKIP_FOREIGN_WAIT 1
+#endif
+#ifndef JK_SHFL_STATS
+#define JK_SHFL_STATS 1
+#endif
+#ifndef JK_LOGITS_MMA
+#define JK_LOGITS_MMA 1
+#endif
+
 namespace {
 
 constexpr int kConsumers = 256;
@@ -371,7 +388,7 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[8][4], uint32_t arow, uin
 // [r*K/KS, (r+1)*K/KS):  partial[16, 8*ncg] = acts[16, K/KS] . Wslice, exchanged inside the unit, and this CTA
 // finishes column pairs [r*ppc, (r+1)*ppc) of the unit: out = epilogue(sum of the KS partials in rank order).
 // ---------------------------------------------------------------------------------------
-enum { EPI_QKV = 0, EPI_PROJ = 1, EPI_FC = 2, EPI_PROJ2 = 3 };
+enum { EPI_QKV = 0, EPI_PROJ = 1, EPI_FC = 2, EPI_PROJ2 = 3, EPI_LOGITS = 4 };
 
 struct GemmArgs {
     const unsigned long long* in;       // LL input [16][K/2]
@@ -383,6 +400,9 @@ struct GemmArgs {
     const long long* ln_in;             // statistics block behind the input (LayerNorm phases)
     long long* ln_out;                  // statistics block of the rows this epilogue writes (residual epilogues)
     int kind;                           // 0: K = width, 1: K = n_state, 2: K = mlp width (thread layout of the staging)
+    int kin;                            // columns of one LL input row (= K, except the logits GEMM: K = 2 * kin)
+    float* lg_out;                      // EPI_LOGITS: fp32 logits of this position, row stride lg_bs
+    long long lg_bs;
 };
 
 __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
@@ -399,8 +419,10 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
         return ring;
     }
     const int K = g.K, N = g.N, epi = g.epi;
-    const int Ks = K >> ksh, k0 = rank * Ks;
-    stage_acts(g.in, K, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in, g.kind, g.pslot);
+    const int Ks = K >> ksh;
+    // the logits GEMM multiplies [y | y] with [hi(x_out) ; lo(x_out)]: its K runs twice over the kin input columns
+    const int k0 = rank * Ks - (rank * Ks >= g.kin ? g.kin : 0);
+    stage_acts(g.in, g.kin, k0, Ks, B, g.flag_in, g.ln, g.gamma, g.beta, g.ln_in, g.kind, g.pslot);
     consumer_sync();
     STAMP(E, g.pslot, 1);
 
@@ -411,6 +433,33 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     const int kpc = kpc_of(ncg);                          // a power of two
     const int astride = (Ks + 8) * 2;
     const uint32_t arow = smem_u32(uni + (lane & 15) * astride + (lane >> 4) * 16);
+#if JK_MMA_ALL_WARPS
+    // The k-steps of this CTA's slice are dealt to the eight warps in contiguous runs (k-step i -> warp i * 8 / nkk), so
+    // every warp multiplies - 4 k-steps each for a K = 2048 / KS = 4 phase instead of four warps with a whole slot each and
+    // four idle.  EVERY warp still waits for every slot and arrives on its empty barrier, in order: the parity protocol of
+    // the ring only holds while no warp is a whole ring ahead of or behind the producer.
+    int k_lo, k_hi;
+    if (nkk >= 8) { k_lo = (warp * nkk) >> 3; k_hi = ((warp + 1) * nkk) >> 3; }
+    else { k_lo = min(warp, nkk); k_hi = min(warp + 1, nkk); }
+    // A warp waits only for the slots it multiplies from when the whole phase fits the ring (a slot index then occurs at
+    // most once per phase, and the CTA barriers between phases keep the warps within one phase of each other, so an early
+    // arrival on a foreign slot's empty barrier always belongs to the barrier's current pass); a phase longer than the ring
+    // (5b_lyrics: 38 slots, 6 in the ring) keeps every warp in the producer's order.  An already-complete try_wait costs
+    // ~90 cycles: three of them per warp per phase were pure overhead.
+    const bool in_order = !JK_SKIP_FOREIGN_WAIT || ((nkk + kpc - 1) >> (31 - __clz(kpc))) > ring.nslot;
+#define JK_MMA_LOOP(NCG)                                                                      \
+    {                                                                                         \
+        _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                        \
+            const int a_ = max(kk0, k_lo), b_ = min(min(kk0 + kpc, nkk), k_hi);               \
+            if (a_ < b_ || in_order) mbar_wait(ring.full(), ring.phase);                       \
+            if (a_ < b_)                                                                      \
+                mma_chunk<NCG>(acc, arow, smem_u32(ring.data()) + lane * 8 + (((a_ - kk0) * NCG) << 8), a_, b_ - a_); \
+            __syncwarp();                                                                      \
+            if (lane == 0) mbar_arrive(ring.empty());                                          \
+            ring.advance();                                                                   \
+        }                                                                                     \
+    }
+#else
     // slot s of this Conv1D is multiplied by warp s % 8 alone.  EVERY warp still waits for the slot and arrives on its
     // empty barrier: the parity protocol of the ring only holds while no warp is a whole ring ahead of or behind the
     // producer (a warp that skipped the handshake of foreign slots aliased phases once a Conv1D had more slots than
@@ -430,6 +479,7 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
             ring.advance();                                                                   \
         }                                                                                     \
     }
+#endif
     switch (ncg) {
         case 1: JK_MMA_LOOP(1) break;
         case 2: JK_MMA_LOOP(2) break;
@@ -442,7 +492,11 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     }
 #undef JK_MMA_LOOP
     STAMP(E, g.pslot, 2);
+#if JK_MMA_ALL_WARPS
+    const int nwarp = min(8, nkk);                                         // warps that multiplied at least one k-step
+#else
     const int nwarp = min(8, (nkk + kpc - 1) >> (31 - __clz(kpc)));       // warps that multiplied at least one slot
+#endif
     float* red = reinterpret_cast<float*>(uni);
     const int ncp = ((nc + 31) & ~31) + 8;
     // partial sums of the unit: [KS ranks][16 rows][64 columns] LL words {fp32, flag}
@@ -489,10 +543,95 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
     const bool two_rows = ppc <= 16;
     const int pl = two_rows ? (lane & 15) : lane;
     const int b_first = two_rows ? 2 * warp + (lane >> 4) : warp, b_step = two_rows ? 16 : 8;
+#if JK_SHFL_STATS
+    {
+        // LayerNorm statistics of the rows this epilogue writes (residual epilogues): a row's column pairs sit in one half
+        // warp (or one warp), so the CTA's contribution to the row is reduced with shuffles and published by one lane with
+        // one red per moment - integer adds, so still order independent - straight from the epilogue: no scratch in shared
+        // memory, no serial summing loop, no CTA barriers around it, and the words are on their way ~0.2 us earlier.
+        const bool active = pl < ppc;
+        const int pr = rank * ppc + (active ? pl : 0);  // pair inside the unit
+        const int gc = g.g0 * 8 + 2 * pr;               // global column of the pair
+        const float2 bias = (active && g.bias) ? *reinterpret_cast<const float2*>(g.bias + gc) : make_float2(0.f, 0.f);
+        // warp-uniform trip count (the two half warps of the 16-pair layout hold rows 2w and 2w + 1; only the row index
+        // differs), so that the shuffles below run under the constant full mask: a run-time member mask compiles to
+        // WARPSYNC.COLLECTIVE, which cost 3.5 us per residual epilogue (profiles/phase_profile_r02e.txt)
+        const int bw0 = two_rows ? 2 * warp : warp;
+#pragma unroll 1
+        for (int bw = bw0; bw < B; bw += b_step) {
+            const int b = bw + (two_rows ? (lane >> 4) : 0);
+            const bool valid = b < B;
+            long long fs = 0, fq = 0;
+            if (active && valid) {
+                float s0 = 0.f, s1 = 0.f;
+                if (KS == 1) {
+                    for (int w = 0; w < nwarp; ++w) {
+                        const float2 v = *reinterpret_cast<const float2*>(red + (size_t)(w * 16 + b) * ncp + 2 * pr);
+                        s0 += v.x; s1 += v.y;
+                    }
+                } else {
+                    ulonglong2 v[4];
+                    unsigned spins = 0;
+                    bool again;
+                    do {
+                        again = false;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < KS) v[q] = ll_ld2(xp_unit + ((size_t)q * 16 + b) * kXpCols + 2 * pr);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < KS) again |= !(ll_ok(v[q].x, g.flag_in) && ll_ok(v[q].y, g.flag_in));
+                        if (again) spin_guard(spins);
+                    } while (again);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < KS) { s0 += __uint_as_float((uint32_t)v[q].x); s1 += __uint_as_float((uint32_t)v[q].y); }
+                }
+                const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
+                __half2 o;
+                if (epi == EPI_QKV) {
+                    o = __floats2half2_rn(y0, y1);
+                } else if (epi == EPI_FC) {                        // quick_gelu (transformer/ops.py:33-35)
+                    o = __floats2half2_rn(quick_gelu_f(y0), quick_gelu_f(y1));
+                } else if (epi != EPI_LOGITS) {
+                    // EPI_PROJ : x1 = fp16(h + a)      EPI_PROJ2 : h = fp16(x1 + m)   (transformer.py:82-83)
+                    const float2 base = res[b * 32 + pl];
+                    const float o0 = h2f_round(base.x + y0), o1 = h2f_round(base.y + y1);
+                    res[b * 32 + pl] = make_float2(o0, o1);
+                    o = __floats2half2_rn(o0, o1);
+                    fs = fx_sum(o0) + fx_sum(o1);
+                    fq = fx_sq(o0) + fx_sq(o1);
+                }
+                if (epi == EPI_LOGITS) {       // fp32 logits (autoregressive.py:226-229): no bias, no rounding
+                    float* lo_ = g.lg_out + (size_t)b * g.lg_bs + gc;      // the caller's strides need not be even
+                    lo_[0] = s0; lo_[1] = s1;
+                } else {
+                    ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
+                }
+            }
+            if (residual) {
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    if (o < 16 || !two_rows) {
+                        fs += __shfl_xor_sync(0xffffffffu, fs, o);
+                        fq += __shfl_xor_sync(0xffffffffu, fq, o);
+                    }
+                }
+                if (pl == 0 && valid) {
+                    red_add_u64(g.ln_out + 16 * b, (1ull << kCntShift) + (unsigned long long)(kSumBias + fs));
+                    red_add_u64(g.ln_out + 16 * b + 1, (1ull << kCntShift) + (unsigned long long)fq);
+                }
+            }
+        }
+    }
+    STAMP(E, g.pslot, 4);
+    consumer_sync();                       // red region is reused by the next phase
+    return ring;
+#endif
     if (pl < ppc) {
         const int pr = rank * ppc + pl;                 // pair inside the unit
         const int gc = g.g0 * 8 + 2 * pr;               // global column of the pair
-        const float2 bias = *reinterpret_cast<const float2*>(g.bias + gc);
+        const float2 bias = g.bias ? *reinterpret_cast<const float2*>(g.bias + gc) : make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int b = b_first; b < B; b += b_step) {
             float s0 = 0.f, s1 = 0.f;
@@ -520,6 +659,11 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (q < KS) { s0 += __uint_as_float((uint32_t)v[q].x); s1 += __uint_as_float((uint32_t)v[q].y); }
+            }
+            if (epi == EPI_LOGITS) {
+                float* lo_ = g.lg_out + (size_t)b * g.lg_bs + gc;
+                lo_[0] = s0; lo_[1] = s1;
+                continue;
             }
             const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
             __half2 o;
@@ -756,12 +900,41 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     {
         const int hw = dhp >> 1, dw = dh >> 1;
         const int nsel = (LD.attn_func == 6) ? 1 : 3;
+#if JK_QKV_POLL_BATCH
+        // up to three words per thread (dh <= 512), ALL issued before the first is examined: one L2 round trip, where a
+        // loop of blocking polls paid one per iteration (two for head_dim 256)
+        const int total = nsel * hw;
+        unsigned long long wv[3];
+        const unsigned long long* wp[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = tid + j * kConsumers;
+            const int sel = (i >= hw) + (i >= 2 * hw), wd = i - sel * hw;
+            wp[j] = (i < total && wd < dw) ? qrow + (size_t)sel * (S >> 1) + wd : nullptr;
+            if (wp[j]) wv[j] = ll_ld1(wp[j]);
+        }
+        unsigned spins = 0;
+        for (;;) {
+            bool again = false;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (wp[j] && !ll_ok(wv[j], flag)) { wv[j] = ll_ld1(wp[j]); again = true; }
+            if (!again) break;
+            spin_guard(spins);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = tid + j * kConsumers;
+            if (i < total) reinterpret_cast<uint32_t*>(qh)[i] = wp[j] ? (uint32_t)wv[j] : 0u;
+        }
+#else
         for (int i = tid; i < nsel * hw; i += kConsumers) {
             const int sel = i / hw, wd = i - sel * hw;
             uint32_t v = 0u;
             if (wd < dw) v = ll_wait1(qrow + (size_t)sel * (S >> 1) + wd, flag);
             reinterpret_cast<uint32_t*>(qh)[sel * hw + wd] = v;
         }
+#endif
     }
     consumer_sync();
     if (G.wrow >= 0 && last_part) {          // cache the current token's k, v
@@ -918,7 +1091,7 @@ __device__ __noinline__ int attn_prefetch(const LayerDev& LD_ref, int B, int c, 
 // ---------------------------------------------------------------------------------------
 // producer warp: walks this CTA's weight stream (and the logits rows) in consumption order
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool do_logits, int c) {
+__device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, int do_logits, int c) {
     if ((threadIdx.x & 31) != 0) return;
     const uint8_t* src = E->streams + (size_t)c * E->stream_stride;
     const int KS = E->KS, u = c >> E->ks_shift;
@@ -948,7 +1121,21 @@ __device__ __noinline__ void producer_loop(const EngineDev* E, Ring ring, bool d
             }
         }
     }
-    if (do_logits) {
+    if (do_logits == 2) {       // logits GEMM: one more Conv1D in the stream
+        const int ncg = E->lg_cols[u].y;
+        if (ncg) {
+            const int nkk = ((2 * E->W) >> E->ks_shift) >> 4, kpc = kpc_of(ncg);
+            for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {
+                const int nk = min(kpc, nkk - kk0);
+                const uint32_t bytes = (uint32_t)nk * ncg * 256u;
+                mbar_wait(ring.empty(), ring.phase ^ 1u);
+                mbar_expect_tx(ring.full(), bytes);
+                tma_bulk_g2s(ring.data(), src, bytes, ring.full());
+                src += bytes;
+                ring.advance();
+            }
+        }
+    } else if (do_logits) {
         const int r0 = E->lrow0[c], r1 = E->lrow0[c + 1];
         const int W = E->W;
         for (int pr = r0; pr < r1; pr += kLogitRowsPerPass) {
@@ -1070,6 +1257,36 @@ __device__ __noinline__ void logits_phase(const StepArgs& A_ref, Ring& ring_ref,
     }
 }
 
+#ifndef JK_CLEANER_WARP
+#define JK_CLEANER_WARP 1
+#endif
+#ifndef JK_ASYNC_RECORD
+#define JK_ASYNC_RECORD 1
+#endif
+// Housekeeping of the LayerNorm statistics blocks, on warp 9 of CTA 0 (a warp of the producer warpgroup that has nothing
+// else to do).  Block i (0 .. 2 * depth) is used once per launch and must be zero again at the next launch.  It may be
+// cleared once a LATER block is complete: every CTA contributes to block i + 1 only after it has consumed block i
+// (program order + data dependence).  The consumer warps of CTA 0 used to do this between their phases - one polled L2
+// round trip on the critical path of CTA 0 (and so of its unit) twice per layer.  The same warp publishes the position
+// and the step count at the end: the final block is complete only when every CTA is through the stack, and every CTA has
+// read both words long before that.
+__device__ __noinline__ void cleaner_loop() {
+    const EngineDev* E = sm_E();
+    const int lane = threadIdx.x & 31, G = E->G, nblk = 2 * E->depth;
+    const int t = *reinterpret_cast<volatile const int*>(E->t);
+    const unsigned step = *reinterpret_cast<volatile const unsigned*>(E->sync + 64);
+    for (int i = 1; i <= nblk; ++i) {
+        if (lane == 0) wait_stat_word(E->lnacc + (size_t)i * 512, G);
+        __syncwarp();
+        (E->lnacc + (size_t)(i - 1) * 512)[16 * (lane >> 1) + (lane & 1)] = 0;
+    }
+    (E->lnacc + (size_t)nblk * 512)[16 * (lane >> 1) + (lane & 1)] = 0;
+    if (lane == 0) {
+        *E->t = t + 1;
+        *(E->sync + 64) = step + 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const EngineDev* __restrict__ Eg, StepArgs A) {
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1094,11 +1311,16 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     }
     __syncthreads();
     const bool do_logits = (A.logits != nullptr) && E->bins > 0;
+    // y = h + x_cond is not an fp16 value: those configurations (upsamplers) keep the fp32 FMA path
+    const bool lg_mma = JK_LOGITS_MMA && E->lg_on && !(E->add_cond_after && A.x_cond);
     // Register reallocation between warpgroups (setmaxnreg, sm_90a+): the block launches with 168 registers per
     // thread (65536 / 384); the producer warpgroup keeps 40 and hands the rest to the two consumer warpgroups.
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 8) producer_loop(Eg, ring, do_logits, c);
+        if (warp == 8) producer_loop(Eg, ring, do_logits ? (lg_mma ? 2 : 1) : 0, c);
+#if JK_CLEANER_WARP
+        else if (warp == 9 && c == 0) cleaner_loop();
+#endif
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -1113,6 +1335,9 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
 #define LN_BLOCK(i_) (E->lnacc + (size_t)(i_) * 512)
     // CTA 0 clears a block for the next launch once a LATER block is complete: every CTA contributes to the later block
     // only after it has consumed the earlier one (program order + data dependence)
+#if JK_CLEANER_WARP
+#define CLEAR_AFTER(clear_, seen_) do { } while (0)       /* cleaner_loop() on warp 9 of CTA 0 */
+#else
 #define CLEAR_AFTER(clear_, seen_)                                                             \
     do {                                                                                       \
         if (c == 0 && tid < 32) {                                                              \
@@ -1121,6 +1346,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             LN_BLOCK(clear_)[16 * (tid >> 1) + (tid & 1)] = 0;                                 \
         }                                                                                      \
     } while (0)
+#endif
     // thread layouts of the activation staging for the three K of a layer (integer divisions: once per launch, not per phase)
     // per-launch constants that need an integer division live in shared memory (not in registers across the phase calls):
     // [7712] p % block_ctx, [7716] p / block_ctx, [7720] CTAs available per (sample, head)
@@ -1211,7 +1437,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_h; ga.out = E->ll_qkv; ga.xp = E->xp[0]; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y;
             ga.ln = 1; ga.epi = EPI_QKV; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr; ga.kind = 0;
+            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr; ga.kind = 0; ga.kin = W; ga.lg_out = nullptr; ga.lg_bs = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(0, 1);
@@ -1221,12 +1447,24 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         // HBM (the weight stream evicts it from L2 every step): issue the loads here so their latency hides
         // behind the attention phase instead of sitting on the dependency chain.
         if (l + 1 < depth) {
+#if JK_ASYNC_RECORD
+            // cp.async: no register sits between the HBM load and the shared-memory store, so no warp stalls on it here;
+            // it is waited for in front of this layer's last Conv1D (whose barriers publish it to the other threads)
+            if (tid < (int)(sizeof(LayerDev) / 4))
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(jk_smem + 1024 + 256 * ((l + 1) & 1) + 4 * tid)),
+                             "l"(reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1]) + tid) : "memory");
+            if (tid >= 32 && tid < 36)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(jk_smem + 1024 + 256 * ((l + 1) & 1) + 128 + 4 * (tid - 32))),
+                             "l"(reinterpret_cast<const uint32_t*>(E->cols + ((size_t)unit * depth + l + 1) * 4) + (tid - 32)) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+#else
             if (tid < (int)(sizeof(LayerDev) / 4))
                 reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1))[tid] =
                     reinterpret_cast<const uint32_t*>(&Eg->layer[l + 1])[tid];
             if (tid >= 32 && tid < 36)
                 reinterpret_cast<uint32_t*>(jk_smem + 1024 + 256 * ((l + 1) & 1) + 128)[tid - 32] =
                     reinterpret_cast<const uint32_t*>(E->cols + ((size_t)unit * depth + l + 1) * 4)[tid - 32];
+#endif
         }
         PHASE_DONE();
         if (l == 1) PROF3(1, 0);
@@ -1247,7 +1485,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_a; ga.out = E->ll_x1; ga.xp = E->xp[1]; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y;
             ga.ln = 0; ga.epi = EPI_PROJ; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 1); ga.kind = 1;
+            ga.ln_out = LN_BLOCK(2 * l + 1); ga.kind = 1; ga.kin = S; ga.lg_out = nullptr; ga.lg_bs = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(2, 1);
@@ -1258,7 +1496,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             ga.in = E->ll_x1; ga.out = E->ll_g; ga.xp = E->xp[2]; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y;
             ga.ln = 1; ga.epi = EPI_FC; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
             ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr; ga.kind = 0;
+            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr; ga.kind = 0; ga.kin = W; ga.lg_out = nullptr; ga.lg_bs = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(3, 1);
@@ -1266,12 +1504,15 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         CLEAR_AFTER(2 * l, 2 * l + 1);
         PHASE_DONE();
         if (l == 1) PROF3(4, 0);
+#if JK_ASYNC_RECORD
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next layer's record (issued a phase and a half ago)
+#endif
         {
             GemmArgs ga;
             ga.in = E->ll_g; ga.out = E->ll_h; ga.xp = E->xp[3]; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y;
             ga.ln = 0; ga.epi = EPI_PROJ2; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl + 1;
             ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 2); ga.kind = 2;
+            ga.ln_out = LN_BLOCK(2 * l + 2); ga.kind = 2; ga.kin = M; ga.lg_out = nullptr; ga.lg_bs = 0;
             ring = gemm_phase(ring, B, ga);
         }
         if (l == 1) PROF3(4, 1);
@@ -1287,18 +1528,36 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
             *reinterpret_cast<float2*>(A.h_out + (size_t)b * W + col) = res[b * 32 + lane];
         }
     }
-    if (do_logits) logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
+    if (do_logits && lg_mma) {
+        // logits GEMM: [y | y] (the final residual stream, fp16-exact) x [hi(x_out) ; lo(x_out)] on the tensor cores, through
+        // the same phase code as every Conv1D; the K-split partial sums (hi and lo halves on different ranks) meet in fp32
+        stage_map_init(2, (2 * W) >> E->ks_shift);
+        consumer_sync();
+        const ushort2 lc = E->lg_cols[unit];
+        GemmArgs ga;
+        ga.in = E->ll_h; ga.out = nullptr; ga.xp = E->xp[0]; ga.K = 2 * W; ga.N = E->bins; ga.g0 = lc.x; ga.ncg = lc.y;
+        ga.ln = 0; ga.epi = EPI_LOGITS; ga.pslot = (int)nph; ga.flag_in = fbase + (uint32_t)depth + 1; ga.flag_out = 0;
+        ga.gamma = nullptr; ga.beta = nullptr; ga.bias = nullptr; ga.ln_in = nullptr; ga.ln_out = nullptr; ga.kind = 2;
+        ga.kin = W; ga.lg_out = A.logits + (size_t)t * A.logits_tstride; ga.lg_bs = A.logits_bstride;
+        ring = gemm_phase(ring, B, ga);
+    } else if (do_logits) {
+        logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
+    }
     // the last LN1 block and the final block: clear them once every CTA is through the stack
     CLEAR_AFTER(2 * depth - 1, 2 * depth);
     if (c == 0) {
         consumer_sync();
+#if !JK_CLEANER_WARP
         if (tid < 32) LN_BLOCK(2 * depth)[16 * (tid >> 1) + (tid & 1)] = 0;
+#endif
         if (tid == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (E->prof_on && nph + 1 < (unsigned)kProfSlots) E->prof[nph + 1] = now;
+#if !JK_CLEANER_WARP
             *E->t = t + 1;
             *(E->sync + 64) = step + 1;
+#endif
         }
     }
 #undef LN_BLOCK
@@ -1344,6 +1603,36 @@ __global__ void pack_gemm_kernel(const T* __restrict__ src, int K, int N, uint8_
         v[1] = to_half<T>(src[(size_t)(k + 1) * N + n]);
         v[2] = to_half<T>(src[(size_t)(k + 8) * N + n]);
         v[3] = to_half<T>(src[(size_t)(k + 9) * N + n]);
+        *reinterpret_cast<uint2*>(dst + (size_t)u * 256 + lane * 8) = *reinterpret_cast<uint2*>(v);
+    }
+}
+
+// logits GEMM: x_out [bins][W] fp32 -> the same per-CTA fragment streams with K' = 2 W: rows k' < W hold hi = fp16(w),
+// rows k' >= W hold lo = fp16(w - hi) (hi + lo carries 22 significant bits; y is an fp16 value, so y.hi + y.lo is the
+// fp32 product up to 2^-22).  Appended to every CTA's stream after the last layer (lg_goff).
+__global__ void pack_logits_kernel(const float* __restrict__ x_out, int W, int bins, uint8_t* streams,
+                                   unsigned long long stream_stride, const ushort2* lg_cols, const uint32_t* lg_goff, int KS) {
+    const int c = blockIdx.x;
+    const ushort2 cg = lg_cols[c / KS];
+    const int g0 = cg.x, ncg = cg.y;
+    if (ncg == 0) return;
+    uint8_t* dst = streams + (size_t)c * stream_stride + (size_t)lg_goff[c] * 16;
+    const int nkk = ((2 * W) / KS) >> 4, kk_first = (c % KS) * nkk;
+    const int total = nkk * ncg * 32;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int lane = i & 31, u = i >> 5;
+        const int j = u % ncg, kk = kk_first + u / ncg;
+        const int n = (g0 + j) * 8 + (lane >> 2);
+        const int k = kk * 16 + (lane & 3) * 2;
+        const int ko[4] = {k, k + 1, k + 8, k + 9};
+        __half v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool lo = ko[e] >= W;
+            const float w = x_out[(size_t)n * W + (lo ? ko[e] - W : ko[e])];
+            const __half hi = __float2half_rn(w);
+            v[e] = lo ? __float2half_rn(w - __half2float(hi)) : hi;
+        }
         *reinterpret_cast<uint2*>(dst + (size_t)u * 256 + lane * 8) = *reinterpret_cast<uint2*>(v);
     }
 }
@@ -1406,6 +1695,7 @@ struct Layout {
     std::vector<ushort2> cols;
     std::vector<uint32_t> goff;
     std::vector<int> lrow;
+    int lg_on;                          // logits GEMM planned: its column groups / stream offsets close `cols` / `goff`
     std::vector<size_t> cache_off;      // per layer (K); V follows
     std::vector<size_t> cache_bytes;
     std::vector<int> cache_rows;
@@ -1493,6 +1783,33 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
             }
         }
     }
+    // logits GEMM (fifth Conv1D, K' = 2 * width: hi and lo fp16 halves of the fp32 x_out): planned when the K-split is even
+    // (a rank's K slice must not straddle the hi / lo boundary), the doubled slice fits the activation tile and no unit
+    // gets more than 8 column groups.  Its records are appended to `cols` ([U] entries) and `goff` ([G] entries).
+    L.lg_on = 0;
+    {
+        const int groups = c.bins / 8;
+        const int Kp = 2 * c.width;
+        const bool ok = c.bins > 0 && c.bins % 8 == 0 && KS >= 2 && (Kp / 16) % KS == 0 && c.width % (Kp / KS) == 0 &&
+                        (size_t)16 * (Kp / KS + 8) * 2 <= (size_t)65536 && (groups + U - 1) / U <= 8 && !getenv("JK_NO_LOGITS_MMA");
+        L.cols.resize((size_t)U * depth * 4 + U, make_ushort2(0, 0));
+        L.goff.resize((size_t)G * depth * 4 + G, 0);
+        if (ok) {
+            L.lg_on = 1;
+            const int base = groups / U, extra = groups % U;
+            std::vector<int> n(U, base);
+            for (int i = 0; i < U; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cum[a] < cum[b]; });
+            for (int i = 0; i < extra; ++i) n[order[i]] += 1;
+            int g0 = 0;
+            for (int u = 0; u < U; ++u) {
+                L.cols[(size_t)U * depth * 4 + u] = make_ushort2((unsigned short)g0, (unsigned short)n[u]);
+                for (int r = 0; r < KS; ++r) L.goff[(size_t)G * depth * 4 + u * KS + r] = (uint32_t)(cum[u] / 16);
+                cum[u] += (unsigned long long)n[u] * (Kp / KS / 16) * 256ull;
+                g0 += n[u];
+            }
+        }
+    }
     unsigned long long mx = 0;
     for (int u = 0; u < U; ++u) mx = std::max(mx, cum[u]);
     JK_REQUIRE(mx / 16 < 0xffffffffull, "stream too long");
@@ -1506,7 +1823,7 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     int RC = attn_tile_rows(L.dh_pad), nslot = 0;
     for (;; RC >>= 1) {
         size_t uni = (size_t)act_rows * (Kmax + 8) * 2;
-        uni = std::max(uni, (size_t)16 * kLogitKT * 4);
+        uni = std::max(uni, (size_t)16 * kLogitKT * 4);       // also covers the logits GEMM's [16][2 W / KS + 8] fp16 tile (<= 64 KB)
         uni = std::max(uni, (size_t)kRedBytes + 2 * 1024 * 8);                       // cross-warp reduction + statistics scratch
         const size_t kv_stage = (size_t)2 * RC * L.dh_pad * 2;                        // one K tile + one V tile
         size_t attn = kv_stage + (size_t)3 * L.dh_pad * 2 + 64 * 4 + (size_t)L.dh_pad * 4 + 64;   // tiles, q/k/v, scores, running output
@@ -1620,8 +1937,9 @@ extern "C" int jk_prior_plan(const jk_prior_config* cfg, int n_sms, jk_prior_pla
     out->k_split = L.KS; out->units = L.U; out->ring_slots = L.nslot; out->smem_bytes = L.smem_bytes; out->tile_rows = L.RC;
     out->arena_bytes = (uint64_t)L.total; out->stream_stride = (uint64_t)L.stream_stride;
     if (cols) {
-        JK_REQUIRE(cols_len >= L.cols.size() * 2, "cols buffer too small: %zu < %zu", cols_len, L.cols.size() * 2);
-        for (size_t i = 0; i < L.cols.size(); ++i) { cols[2 * i] = L.cols[i].x; cols[2 * i + 1] = L.cols[i].y; }
+        const size_t ncols = (size_t)L.U * cfg->depth * 4;       // the layers' records (the logits GEMM's follow in L.cols)
+        JK_REQUIRE(cols_len >= ncols * 2, "cols buffer too small: %zu < %zu", cols_len, ncols * 2);
+        for (size_t i = 0; i < ncols; ++i) { cols[2 * i] = L.cols[i].x; cols[2 * i + 1] = L.cols[i].y; }
     }
     return 0;
 }
@@ -1665,6 +1983,9 @@ extern "C" int jk_prior_create(const jk_prior_config* cfg, void* arena, size_t a
     p->d_cols = (ushort2*)(A + L.off_cols);
     p->d_goff = (uint32_t*)(A + L.off_goff);
     E.lrow0 = (const int*)(A + L.off_lrow);
+    E.lg_on = L.lg_on; p->lg_on = L.lg_on;
+    E.lg_cols = (const ushort2*)(A + L.off_cols) + (size_t)L.U * cfg->depth * 4;
+    E.lg_goff = (const uint32_t*)(A + L.off_goff) + (size_t)G * cfg->depth * 4;
     E.streams = A + L.off_streams; E.stream_stride = L.stream_stride;
     E.ll_h = (unsigned long long*)(A + L.off_h); E.ll_x1 = (unsigned long long*)(A + L.off_x1);
     E.ll_qkv = (unsigned long long*)(A + L.off_qkv); E.ll_a = (unsigned long long*)(A + L.off_a);
@@ -1811,6 +2132,12 @@ extern "C" int jk_prior_set_embeddings(jk_prior* p, const float* x_emb, const fl
     JK_REQUIRE(p, "null engine");
     p->host.x_emb = x_emb; p->host.pos_emb = pos_emb; p->host.x_out = x_out; p->host.start_token = start_token;
     JK_CHECK_CUDA(cudaMemcpy(p->dev, &p->host, sizeof(EngineDev), cudaMemcpyHostToDevice));
+    if (p->lg_on && x_out) {       // logits GEMM: hi / lo fp16 fragment streams of x_out, behind every CTA's last layer
+        pack_logits_kernel<<<p->G, 256>>>(x_out, p->cfg.width, p->cfg.bins, (uint8_t*)p->host.streams, p->host.stream_stride,
+                                          p->host.lg_cols, p->host.lg_goff, p->host.KS);
+        JK_CHECK_CUDA(cudaGetLastError());
+        JK_CHECK_CUDA(cudaDeviceSynchronize());
+    }
     return 0;
 }
 

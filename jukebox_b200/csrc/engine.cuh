@@ -41,6 +41,11 @@ struct EngineDev {
     int* t;
     const float *x_emb, *pos_emb, *x_out, *start_token;
     const int* lrow0;               // [G+1] logits rows per CTA (prefix)
+    // logits as a fifth Conv1D on the tensor cores (decode_engine.cu "logits GEMM"): 0 when the configuration keeps
+    // the fp32 FMA path; column groups per unit [U] and stream offsets per CTA [G] (16-byte units)
+    int lg_on;
+    const ushort2* lg_cols;
+    const uint32_t* lg_goff;
     LayerDev layer[JK_MAX_DEPTH];
 };
 
@@ -62,6 +67,7 @@ struct jk_prior {
     int t_host;
     std::vector<ushort2> cols;       // [U][depth][4]
     std::vector<uint32_t> goff;      // [G][depth][4] per-GEMM stream offsets (16-B units)
+    int lg_on;                       // logits GEMM planned (engine.cuh)
     uint32_t* d_goff;
     ushort2* d_cols;
     // arena sub-allocations for per-layer small params

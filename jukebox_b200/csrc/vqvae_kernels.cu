@@ -954,9 +954,10 @@ __global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P, int span
         __syncthreads();
         const long long off = span >= 0 ? min_off : (pass == 0 ? P.tap_off[0] : pass == 1 ? P.tap_off[1] : pass == 2 ? P.tap_off[2] : P.tap_off[3]);
         const int rows = span >= 0 ? 256 + span : 256;
+        const int c4sh = (c4n & (c4n - 1)) == 0 ? 31 - __clz(c4n) : -1;      // c_in = 32 / 64: shifts, not a division per chunk
 #pragma unroll 4
         for (int i = threadIdx.x; i < rows * c4n; i += 256) {
-            const int r = i / c4n, c4 = i - r * c4n;
+            const int r = c4sh >= 0 ? (i >> c4sh) : i / c4n, c4 = i - r * c4n;
             const long long tp = span >= 0 ? t0 + r + off : (t0 + r) * P.in_stride + off;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tp >= 0 && tp < P.t_in) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)tp * CI) + c4);
@@ -969,6 +970,16 @@ __global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P, int span
             const int toff = tap == 0 ? P.tap_off[0] : tap == 1 ? P.tap_off[1] : tap == 2 ? P.tap_off[2] : P.tap_off[3];
             const float* xr = xs + (size_t)(threadIdx.x + (span >= 0 ? toff - min_off : 0)) * XS;
             const float* wr = wsm + (size_t)tap * CI * CO;
+            if (CO == 1) {      // the audio output conv: four weights per LDS.128 (was one broadcast LDS.32 per FMA); same order
+#pragma unroll 4
+                for (int c = 0; c < CI; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+                    const float4 w4 = *reinterpret_cast<const float4*>(wr + c);
+                    acc[0] = fmaf(v.x, w4.x, acc[0]); acc[0] = fmaf(v.y, w4.y, acc[0]);
+                    acc[0] = fmaf(v.z, w4.z, acc[0]); acc[0] = fmaf(v.w, w4.w, acc[0]);
+                }
+                continue;
+            }
             for (int c = 0; c < CI; c += 4) {            // same accumulation order as the tile kernel: tap, then channel
                 const float4 v = *reinterpret_cast<const float4*>(xr + c);
                 const float xv[4] = {v.x, v.y, v.z, v.w};
@@ -1146,6 +1157,11 @@ extern "C" int jk_resblock_cl(const float* x, float* out, float* tmp, const floa
     return jk_conv1d_cl(&a, stream);
 }
 
+namespace jk {
+int resblock_t5(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2, int n,
+                long long T, int C, int dil, float rs, cudaStream_t stream);      // vqvae_t5.cu
+}
+
 extern "C" int jk_resblock_tc(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
                               int n, int64_t T, int C, int dilation, float res_scale, jk_stream_t stream) {
     JK_REQUIRE(x && out && w1 && w2 && b1 && b2, "null argument");
@@ -1155,6 +1171,11 @@ extern "C" int jk_resblock_tc(const float* x, float* out, const float* w1, const
         if (C == 64) return launch_resblock_tc<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
         if (C == 32) return launch_resblock_tc<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
     }
+    // tcgen05 + TMA version (vqvae_t5.cu): whole 128-position MMA tiles, TMA needs 16-byte aligned rows.  JK_RESBLOCK_T5=0
+    // keeps the mma.sync kernel (A/B runs).
+    static const bool t5 = !(getenv("JK_RESBLOCK_T5") && atoi(getenv("JK_RESBLOCK_T5")) == 0);
+    if (t5 && (C == 64 || C == 32) && T >= 128 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0)
+        return jk::resblock_t5(x, out, w1, b1, w2, b2, n, T, C, dilation, res_scale, (cudaStream_t)stream);
     if (C == 64) return launch_resblock_h2<64>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
     if (C == 32) return launch_resblock_h2<32>(x, out, w1, b1, w2, b2, n, T, dilation, res_scale, (cudaStream_t)stream);
     JK_REQUIRE(false, "jk_resblock_tc: C must be 32 or 64 (got %d)", C);

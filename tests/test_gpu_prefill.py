@@ -61,7 +61,7 @@ CASES = [
     (0, 256, 3, 4, 48, None, None, 17),  # dense
     (2, 320, 6, 2, 64, 4, None, 33),    # K tail: n_state 80 is not a multiple of the 64-wide tcgen05 K block (5b: 1200, upsamplers: 480)
     (2, 256, 6, 1, 1024, 8, None, 700),  # a long run of given tokens (continuation windows re-prime thousands)
-    (2, 2400, 3, 4, 64, 4, None, 33),   # head_dim 150 (5b_lyrics): head rows are not 16-byte aligned
+    (2, 4800, 3, 8, 64, 4, None, 33),   # 5b_lyrics geometry: n_state 1200, head_dim 150 - head rows are not 16-byte aligned
     (0, 1024, 2, 1, 160, None, None, 150),  # head_dim 256, dense: several key tiles per query tile
 ]
 

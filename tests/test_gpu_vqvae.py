@@ -108,11 +108,13 @@ def test_decode_is_batch_independent_and_linear_in_out_bias():
     assert torch.equal(a[2:3], c)
 
 
-@pytest.mark.parametrize("C,dil,T", [(64, 1, 1000), (64, 2187, 5000), (32, 27, 777), (32, 1, 64), (64, 9, 65)])
+@pytest.mark.parametrize("C,dil,T", [(64, 1, 1000), (64, 2187, 5000), (32, 27, 777), (32, 1, 64), (64, 9, 65),
+                                     (64, 27, 128), (32, 243, 4101), (64, 729, 20000), (32, 3, 129)])
 def test_tensor_core_resblock_matches_exact_fma_kernel(C, dil, T):
-    """jk_resblock_tc (split-precision tensor-core block, decoder side: fp16 x 3 on mma.sync.m16n8k16; the 3xTF32 kernel
-    with JK_RESBLOCK_TF32=1) against jk_resblock_cl (exact fp32 FMAs): same block (resnet.py:27-44), fp32-level
-    agreement; ragged T, dilations beyond the tile, both channel counts"""
+    """jk_resblock_tc (split-precision tensor-core block, decoder side) against jk_resblock_cl (exact fp32 FMAs): same block
+    (resnet.py:27-44), fp32-level agreement; ragged T, dilations beyond the tile, both channel counts.  T >= 128 runs the
+    tcgen05 / TMA kernel (vqvae_t5.cu: 128-position MMA tiles, out-of-range rows zero-filled by the tensor map), shorter
+    clips the fp16 x 3 mma.sync kernel (JK_RESBLOCK_T5=0 / JK_RESBLOCK_TF32=1 select the older kernels for A/B runs)"""
     import ctypes as Cc
     from jukebox_b200._lib import lib, check, ptr, stream_ptr
     g = torch.Generator(device="cuda").manual_seed(C + dil)

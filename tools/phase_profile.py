@@ -72,6 +72,11 @@ def main():
             rows.append([(s1 - s0), (s2 - s1), (s3 - s2), (s4 - s3)])
         r = np.mean(rows, 0) / mhz
         print(f"     {nm:8s}: {r[0]:6.2f} | {r[1]:6.2f} | {r[2]:6.2f} | {r[3]:6.2f}")
+    sl = 1 + 5 * depth                 # the logits GEMM (when the engine plans one) stamps the slot after the last layer
+    if p2[sl, 4] > p2[sl, 0] > 0:
+        s0, s1, s2, s3, s4 = p2[sl, :5]
+        print(f"     logits  : {(s1 - s0) / mhz:6.2f} | {(s2 - s1) / mhz:6.2f} | {(s3 - s2) / mhz:6.2f} | {(s4 - s3) / mhz:6.2f}   "
+              f"(polled loads in at {(p2[sl, 6] - s0) / mhz:5.2f})")
     print("  CTA 0, staging detail (us from phase entry): statistics ready | own polled loads in | past the statistics barrier | staged + barrier")
     for j, nm in ((0, "LN+QKV"), (2, "proj"), (3, "LN+FC"), (4, "proj2")):
         rows = []
