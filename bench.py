@@ -640,12 +640,12 @@ def main():
     for p0 in octile:
         eng.reset(p0)
         for _ in range(3):
-            eng.step(n, tokens=toks, y_cond=win.y_cond, x_cond=win.x_cond, logits=lbuf)
+            eng.step(n, tokens=toks, y_cond=win.y_cond, x_cond=win.x_cond, logits=lbuf, logit_bias=win.logit_bias)
         eng.reset(p0)
         torch.cuda.synchronize()
         for i in range(reps):
             ev[2 * i].record()
-            eng.step(n, tokens=toks, y_cond=win.y_cond, x_cond=win.x_cond, logits=lbuf)
+            eng.step(n, tokens=toks, y_cond=win.y_cond, x_cond=win.x_cond, logits=lbuf, logit_bias=win.logit_bias)
             ev[2 * i + 1].record()
         torch.cuda.synchronize()
         kern_ms += sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps))
@@ -714,8 +714,12 @@ def main():
             if enc is not None:
                 eng.set_encoder_kv(torch.from_numpy(enc).cuda())
             got = []
+            gb = None       # x_cond . x_out^T, as SamplingWindow computes it for the tensor-core logits product
+            if gx is not None and ca.add_cond_after_transformer and eng.has_logits_gemm:
+                from jukebox_b200.transformer import f32 as _f32
+                gb = _f32.linear_nk(gx.reshape(n, cfg["width"]), ca.x_out.weight).view(n, 1, ca.bins)
             for _ in range(np_pos):
-                eng.step(n, tokens=gt, y_cond=gy, x_cond=gx, logits=glog)
+                eng.step(n, tokens=gt, y_cond=gy, x_cond=gx, logits=glog, logit_bias=gb)
                 got.append(glog.clone())
             ca.transformer.del_cache()
             got = torch.stack(got, 1).cpu().numpy()

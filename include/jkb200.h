@@ -112,6 +112,10 @@ int jk_prior_set_embeddings(jk_prior* p, const float* x_emb, const float* pos_em
 int jk_prior_reset(jk_prior* p, int t0, jk_stream_t stream);
 /* encoder K/V for attn_func 6 layers: c_enc_kv(encoder_kv) computed once per window
  * (factored_attention.py:273-287).  encoder_kv: fp32 [n, encoder_dims, W] */
+/* 1 if this engine multiplies the logits on the tensor cores (hi / lo fp16 split of x_out; needs an even K split and
+ * bins > 0), i.e. if jk_step_args.logit_bias is worth computing */
+int jk_prior_has_logits_gemm(const jk_prior* p, int* on);
+
 int jk_prior_set_encoder_kv(jk_prior* p, const float* encoder_kv, int n_samples, jk_stream_t stream);
 
 typedef struct jk_step_args {
@@ -129,6 +133,15 @@ typedef struct jk_step_args {
     float* logits;                /* fp32: logits[b*logits_bstride + t*logits_tstride + v] */
     int64_t logits_bstride;
     int64_t logits_tstride;       /* 0 to overwrite the same [n, bins] buffer every step */
+    /* optional: x_cond . x_out^T of every position, computed once per window by the caller (the logits are linear in the
+     * activation: (h + x_cond) . x_out^T = h . x_out^T + logit_bias).  With it, priors that add x_cond behind the stack
+     * (autoregressive.py:226-227: every label-conditioned prior) still take the tensor-core logits product, whose
+     * activation operand must be an fp16 value; NULL keeps the fp32 product of h + x_cond.
+     * logit_bias[b*logit_bias_bstride + t*logit_bias_tstride + v]; ignored when the engine has no logits GEMM
+     * (jk_prior_has_logits_gemm). */
+    const float* logit_bias;
+    int64_t logit_bias_bstride;
+    int64_t logit_bias_tstride;
 } jk_step_args;
 
 /* Chunked prefill of the given (prime) tokens: positions 0 .. n_positions-1 of every sample through all

@@ -52,7 +52,8 @@ class StepArgs(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("x_in", C.c_void_p), ("tokens", C.c_void_p),
                 ("tok_stride", C.c_int64), ("y_cond", C.c_void_p), ("x_cond", C.c_void_p),
                 ("x_cond_len", C.c_int64), ("h_out", C.c_void_p), ("logits", C.c_void_p),
-                ("logits_bstride", C.c_int64), ("logits_tstride", C.c_int64)]
+                ("logits_bstride", C.c_int64), ("logits_tstride", C.c_int64), ("logit_bias", C.c_void_p),
+                ("logit_bias_bstride", C.c_int64), ("logit_bias_tstride", C.c_int64)]
 
 
 class PrefillArgs(C.Structure):
@@ -88,6 +89,7 @@ SIGNATURES = {
     "jk_prior_prefill_capacity": (_I, [_P, C.POINTER(C.c_int)]),
     "jk_prior_prefill": (_I, [_P, C.POINTER(PrefillArgs), _P]),
     "jk_prior_position": (_I, [_P, C.POINTER(C.c_int)]),
+    "jk_prior_has_logits_gemm": (_I, [_P, C.POINTER(C.c_int)]),
     "jk_prior_debug_buffer": (_I, [_P, _I, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "jk_conv1d_prefill_f16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "jk_sample_categorical": (_I, [_P, _L, _I, _I, _F, C.c_uint64, _I, _P, _L, _P]),

@@ -93,6 +93,8 @@ struct StepArgs {
     float* h_out;
     float* logits;
     long long logits_bstride, logits_tstride;
+    const float* logit_bias;            // x_cond . x_out^T per position (jkb200.h), or NULL
+    long long lb_bstride, lb_tstride;
 };
 
 // The one dynamic shared-memory block of the decode kernel.  Every device function derives its
@@ -403,10 +405,55 @@ struct GemmArgs {
     int kin;                            // columns of one LL input row (= K, except the logits GEMM: K = 2 * kin)
     float* lg_out;                      // EPI_LOGITS: fp32 logits of this position, row stride lg_bs
     long long lg_bs;
+    const float* lb;                    // EPI_LOGITS: logit bias of this position (or NULL), row stride lb_bs
+    long long lb_bs;
 };
 
-__device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   // by value: registers, not local memory
+// per-launch record of the logits GEMM in the shared-memory header (written once by the kernel prologue)
+struct LogitsRec {
+    float* lg_out;              // logits of this position
+    long long lg_bs;
+    const float* lb;            // logit bias of this position or NULL
+    long long lb_bs;
+    ushort2 cols;               // column groups of this unit
+};
+__device__ __forceinline__ LogitsRec* sm_lrec() { return reinterpret_cast<LogitsRec*>(jk_smem + 7744); }
+
+// One Conv1D of layer l (or the logits GEMM), identified by its epilogue.  The argument record is assembled HERE from the
+// descriptor / layer record / column table in shared memory: passed by value it had grown past what the call ABI keeps in
+// registers (896 bytes of stack), and with the shared-memory carve-out at its maximum every local-memory access is an L2
+// round trip - the step went from 1.95 to 2.5 ms (profiles/decode_variants_ab_r02b.txt).
+__device__ __noinline__ Ring gemm_phase(Ring ring, int B, int epi_, int l, int pslot_, uint32_t fl) {
     const EngineDev* E = sm_E();
+    GemmArgs g;
+    {
+        const LayerDev& LD = *sm_layer(l);
+        const ushort2* cl = reinterpret_cast<const ushort2*>(jk_smem + 1024 + 256 * (l & 1) + 128);
+        const int W = E->W, S = E->S, M = E->M;
+        long long* lnb = E->lnacc + (size_t)(2 * l) * 512;
+        g.epi = epi_; g.pslot = pslot_; g.flag_in = fl; g.flag_out = fl;
+        g.gamma = nullptr; g.beta = nullptr; g.ln_in = nullptr; g.ln_out = nullptr; g.ln = 0;
+        g.lg_out = nullptr; g.lg_bs = 0; g.lb = nullptr; g.lb_bs = 0;
+        if (epi_ == EPI_QKV) {
+            g.in = E->ll_h; g.out = E->ll_qkv; g.xp = E->xp[0]; g.K = W; g.N = (LD.attn_func == 6) ? S : 3 * S;
+            g.g0 = cl[0].x; g.ncg = cl[0].y; g.ln = 1; g.gamma = LD.ln0_g; g.beta = LD.ln0_b; g.bias = LD.b_qkv;
+            g.ln_in = lnb; g.kind = 0; g.kin = W;
+        } else if (epi_ == EPI_PROJ) {
+            g.in = E->ll_a; g.out = E->ll_x1; g.xp = E->xp[1]; g.K = S; g.N = W; g.g0 = cl[1].x; g.ncg = cl[1].y;
+            g.bias = LD.b_o; g.ln_out = lnb + 512; g.kind = 1; g.kin = S;
+        } else if (epi_ == EPI_FC) {
+            g.in = E->ll_x1; g.out = E->ll_g; g.xp = E->xp[2]; g.K = W; g.N = M; g.g0 = cl[2].x; g.ncg = cl[2].y;
+            g.ln = 1; g.gamma = LD.ln1_g; g.beta = LD.ln1_b; g.bias = LD.b_1; g.ln_in = lnb + 512; g.kind = 0; g.kin = W;
+        } else if (epi_ == EPI_PROJ2) {
+            g.in = E->ll_g; g.out = E->ll_h; g.xp = E->xp[3]; g.K = M; g.N = W; g.g0 = cl[3].x; g.ncg = cl[3].y;
+            g.bias = LD.b_2; g.ln_out = lnb + 1024; g.flag_out = fl + 1; g.kind = 2; g.kin = M;
+        } else {       // EPI_LOGITS: [y | y] x [hi(x_out) ; lo(x_out)], see the kernel
+            const LogitsRec* lr = sm_lrec();
+            g.in = E->ll_h; g.out = nullptr; g.xp = E->xp[0]; g.K = 2 * W; g.N = E->bins; g.g0 = lr->cols.x; g.ncg = lr->cols.y;
+            g.bias = nullptr; g.kind = 2; g.kin = W; g.flag_out = 0;
+            g.lg_out = lr->lg_out; g.lg_bs = lr->lg_bs; g.lb = lr->lb; g.lb_bs = lr->lb_bs;
+        }
+    }
     uint8_t* uni = sm_uni();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KS = E->KS, ksh = E->ks_shift, c = blockIdx.x, rank = c & (KS - 1);
@@ -604,7 +651,10 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
                 }
                 if (epi == EPI_LOGITS) {       // fp32 logits (autoregressive.py:226-229): no bias, no rounding
                     float* lo_ = g.lg_out + (size_t)b * g.lg_bs + gc;      // the caller's strides need not be even
-                    lo_[0] = s0; lo_[1] = s1;
+                    const float* lb_ = g.lb ? g.lb + (size_t)b * g.lb_bs + gc : nullptr;
+                    // bins need not be a multiple of 8 (1b_lyrics: 2127): the last column group is padded with zero weights
+                    if (gc < N) lo_[0] = s0 + (lb_ ? lb_[0] : 0.f);
+                    if (gc + 1 < N) lo_[1] = s1 + (lb_ ? lb_[1] : 0.f);
                 } else {
                     ll_st(g.out + (size_t)b * (N >> 1) + (gc >> 1), *reinterpret_cast<const uint32_t*>(&o), g.flag_out);
                 }
@@ -662,7 +712,9 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, const GemmArgs g) {   
             }
             if (epi == EPI_LOGITS) {
                 float* lo_ = g.lg_out + (size_t)b * g.lg_bs + gc;
-                lo_[0] = s0; lo_[1] = s1;
+                const float* lb_ = g.lb ? g.lb + (size_t)b * g.lb_bs + gc : nullptr;
+                if (gc < N) lo_[0] = s0 + (lb_ ? lb_[0] : 0.f);
+                if (gc + 1 < N) lo_[1] = s1 + (lb_ ? lb_[1] : 0.f);
                 continue;
             }
             const float y0 = h2f_round(s0 + bias.x), y1 = h2f_round(s1 + bias.y);     // Conv1D output, rounded once to fp16
@@ -1312,7 +1364,8 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
     __syncthreads();
     const bool do_logits = (A.logits != nullptr) && E->bins > 0;
     // y = h + x_cond is not an fp16 value: those configurations (upsamplers) keep the fp32 FMA path
-    const bool lg_mma = JK_LOGITS_MMA && E->lg_on && !(E->add_cond_after && A.x_cond);
+    // (unless the caller supplies x_cond . x_out^T, the logit bias of jkb200.h: the product is linear in the activation)
+    const bool lg_mma = JK_LOGITS_MMA && E->lg_on && (!(E->add_cond_after && A.x_cond) || A.logit_bias);
     // Register reallocation between warpgroups (setmaxnreg, sm_90a+): the block launches with 168 registers per
     // thread (65536 / 384); the producer warpgroup keeps 40 and hands the rest to the two consumer warpgroups.
     if (warp >= 8) {
@@ -1432,14 +1485,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         const int pre = attn_prefetch(LD, B, c, t, PM, PD, GMAX);
         // a fresh argument record per phase: nothing of it stays live across the calls in between
         if (l == 1) PROF3(0, 0);
-        {
-            GemmArgs ga;
-            ga.in = E->ll_h; ga.out = E->ll_qkv; ga.xp = E->xp[0]; ga.K = W; ga.N = Nqkv; ga.g0 = cl[0].x; ga.ncg = cl[0].y;
-            ga.ln = 1; ga.epi = EPI_QKV; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
-            ga.gamma = LD.ln0_g; ga.beta = LD.ln0_b; ga.bias = LD.b_qkv;
-            ga.ln_in = LN_BLOCK(2 * l); ga.ln_out = nullptr; ga.kind = 0; ga.kin = W; ga.lg_out = nullptr; ga.lg_bs = 0;
-            ring = gemm_phase(ring, B, ga);
-        }
+        ring = gemm_phase(ring, B, EPI_QKV, l, (int)nph, fl);
         if (l == 1) PROF3(0, 1);
         // LN1 statistics of the previous layer: consumed once this layer's LN0 block is complete
         if (l > 0) CLEAR_AFTER(2 * l - 1, 2 * l);
@@ -1480,25 +1526,11 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         if (l == 1) PROF3(1, 1);
         PHASE_DONE();
         if (l == 1) PROF3(2, 0);
-        {
-            GemmArgs ga;
-            ga.in = E->ll_a; ga.out = E->ll_x1; ga.xp = E->xp[1]; ga.K = S; ga.N = W; ga.g0 = cl[1].x; ga.ncg = cl[1].y;
-            ga.ln = 0; ga.epi = EPI_PROJ; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
-            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_o; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 1); ga.kind = 1; ga.kin = S; ga.lg_out = nullptr; ga.lg_bs = 0;
-            ring = gemm_phase(ring, B, ga);
-        }
+        ring = gemm_phase(ring, B, EPI_PROJ, l, (int)nph, fl);
         if (l == 1) PROF3(2, 1);
         PHASE_DONE();
         if (l == 1) PROF3(3, 0);
-        {
-            GemmArgs ga;
-            ga.in = E->ll_x1; ga.out = E->ll_g; ga.xp = E->xp[2]; ga.K = W; ga.N = M; ga.g0 = cl[2].x; ga.ncg = cl[2].y;
-            ga.ln = 1; ga.epi = EPI_FC; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl;
-            ga.gamma = LD.ln1_g; ga.beta = LD.ln1_b; ga.bias = LD.b_1;
-            ga.ln_in = LN_BLOCK(2 * l + 1); ga.ln_out = nullptr; ga.kind = 0; ga.kin = W; ga.lg_out = nullptr; ga.lg_bs = 0;
-            ring = gemm_phase(ring, B, ga);
-        }
+        ring = gemm_phase(ring, B, EPI_FC, l, (int)nph, fl);
         if (l == 1) PROF3(3, 1);
         // LN0 statistics of this layer: consumed once its LN1 block is complete
         CLEAR_AFTER(2 * l, 2 * l + 1);
@@ -1507,14 +1539,7 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
 #if JK_ASYNC_RECORD
         asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next layer's record (issued a phase and a half ago)
 #endif
-        {
-            GemmArgs ga;
-            ga.in = E->ll_g; ga.out = E->ll_h; ga.xp = E->xp[3]; ga.K = M; ga.N = W; ga.g0 = cl[3].x; ga.ncg = cl[3].y;
-            ga.ln = 0; ga.epi = EPI_PROJ2; ga.pslot = (int)nph; ga.flag_in = fl; ga.flag_out = fl + 1;
-            ga.gamma = nullptr; ga.beta = nullptr; ga.bias = LD.b_2; ga.ln_in = nullptr;
-            ga.ln_out = LN_BLOCK(2 * l + 2); ga.kind = 2; ga.kin = M; ga.lg_out = nullptr; ga.lg_bs = 0;
-            ring = gemm_phase(ring, B, ga);
-        }
+        ring = gemm_phase(ring, B, EPI_PROJ2, l, (int)nph, fl);
         if (l == 1) PROF3(4, 1);
         PHASE_DONE();
     }
@@ -1533,13 +1558,14 @@ __global__ void __launch_bounds__(kThreads, 1) jk_decode_step_kernel(const Engin
         // the same phase code as every Conv1D; the K-split partial sums (hi and lo halves on different ranks) meet in fp32
         stage_map_init(2, (2 * W) >> E->ks_shift);
         consumer_sync();
-        const ushort2 lc = E->lg_cols[unit];
-        GemmArgs ga;
-        ga.in = E->ll_h; ga.out = nullptr; ga.xp = E->xp[0]; ga.K = 2 * W; ga.N = E->bins; ga.g0 = lc.x; ga.ncg = lc.y;
-        ga.ln = 0; ga.epi = EPI_LOGITS; ga.pslot = (int)nph; ga.flag_in = fbase + (uint32_t)depth + 1; ga.flag_out = 0;
-        ga.gamma = nullptr; ga.beta = nullptr; ga.bias = nullptr; ga.ln_in = nullptr; ga.ln_out = nullptr; ga.kind = 2;
-        ga.kin = W; ga.lg_out = A.logits + (size_t)t * A.logits_tstride; ga.lg_bs = A.logits_bstride;
-        ring = gemm_phase(ring, B, ga);
+        if (tid == 0) {
+            LogitsRec* lr = sm_lrec();
+            lr->lg_out = A.logits + (size_t)t * A.logits_tstride; lr->lg_bs = A.logits_bstride;
+            lr->lb = (E->add_cond_after && A.x_cond) ? A.logit_bias + (size_t)t * A.lb_tstride : nullptr; lr->lb_bs = A.lb_bstride;
+            lr->cols = E->lg_cols[unit];
+        }
+        consumer_sync();
+        ring = gemm_phase(ring, B, EPI_LOGITS, depth - 1, (int)nph, fbase + (uint32_t)depth + 1);
     } else if (do_logits) {
         logits_phase(A, ring, c, t, fbase + (uint32_t)depth + 1);
     }
@@ -1629,7 +1655,7 @@ __global__ void pack_logits_kernel(const float* __restrict__ x_out, int W, int b
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const bool lo = ko[e] >= W;
-            const float w = x_out[(size_t)n * W + (lo ? ko[e] - W : ko[e])];
+            const float w = n < bins ? x_out[(size_t)n * W + (lo ? ko[e] - W : ko[e])] : 0.f;
             const __half hi = __float2half_rn(w);
             v[e] = lo ? __float2half_rn(w - __half2float(hi)) : hi;
         }
@@ -1788,9 +1814,9 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     // gets more than 8 column groups.  Its records are appended to `cols` ([U] entries) and `goff` ([G] entries).
     L.lg_on = 0;
     {
-        const int groups = c.bins / 8;
+        const int groups = (c.bins + 7) / 8;           // a ragged last group is padded with zero weights
         const int Kp = 2 * c.width;
-        const bool ok = c.bins > 0 && c.bins % 8 == 0 && KS >= 2 && (Kp / 16) % KS == 0 && c.width % (Kp / KS) == 0 &&
+        const bool ok = c.bins > 0 && KS >= 2 && (Kp / 16) % KS == 0 && c.width % (Kp / KS) == 0 &&
                         (size_t)16 * (Kp / KS + 8) * 2 <= (size_t)65536 && (groups + U - 1) / U <= 8 && !getenv("JK_NO_LOGITS_MMA");
         L.cols.resize((size_t)U * depth * 4 + U, make_ushort2(0, 0));
         L.goff.resize((size_t)G * depth * 4 + G, 0);
@@ -2190,11 +2216,18 @@ extern "C" int jk_prior_step(jk_prior* p, const jk_step_args* a, jk_stream_t str
     A.n = a->n_samples; A.x_in = a->x_in; A.tokens = (const long long*)a->tokens; A.tok_stride = a->tok_stride;
     A.y_cond = a->y_cond; A.x_cond = a->x_cond; A.x_cond_len = a->x_cond_len ? a->x_cond_len : 1;
     A.h_out = a->h_out; A.logits = a->logits; A.logits_bstride = a->logits_bstride; A.logits_tstride = a->logits_tstride;
+    A.logit_bias = a->logit_bias; A.lb_bstride = a->logit_bias_bstride; A.lb_tstride = a->logit_bias_tstride;
     const EngineDev* E = p->dev;
     void* args[2] = {(void*)&E, (void*)&A};
     JK_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)jk_decode_step_kernel, dim3(p->G), dim3(kThreads), args,
                                               (size_t)p->smem_bytes, stream));
     p->t_host += 1;
+    return 0;
+}
+
+extern "C" int jk_prior_has_logits_gemm(const jk_prior* p, int* on) {
+    JK_REQUIRE(p && on, "null argument");
+    *on = (JK_LOGITS_MMA && p->lg_on) ? 1 : 0;
     return 0;
 }
 

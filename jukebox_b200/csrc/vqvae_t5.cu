@@ -32,8 +32,20 @@ using namespace jk;
 
 namespace {
 
+#ifndef JK_T5_PREFETCH
+#define JK_T5_PREFETCH 1
+#endif
 constexpr int kBM = 128;                  // positions per tile = MMA M
-constexpr int kThreadsT5 = 320;
+// converter groups of 4 warps (group g converts the taps whose counter is g mod 2): two for C = 32, one for C = 64
+// (A/B on one box, profiles/resblock_t5_variants_r02.txt); JK_T5_CONV_GROUPS overrides both
+template <int C>
+struct T5Groups {
+#ifdef JK_T5_CONV_GROUPS
+    static constexpr int value = JK_T5_CONV_GROUPS;
+#else
+    static constexpr int value = C == 64 ? 1 : 2;
+#endif
+};
 constexpr float kWScaleT5 = 256.f, kWInvT5 = 1.f / 256.f;
 
 template <int C>
@@ -42,11 +54,12 @@ struct T5 {
     static constexpr int kW1 = 3 * kWBlock, kW2 = kWBlock;   // bytes per plane
     static constexpr int kATile = kBM * 128;                 // one operand plane of a tap / hidden tile (128-byte rows)
     static constexpr int kFTile = kBM * C * 4;               // fp32 tap tile as TMA delivers it
+    static constexpr int kFS = C == 64 ? 2 : 4;              // stages of the fp32 ring (what shared memory leaves room for)
     static constexpr int offW1h = 0, offW1l = kW1, offW2h = 2 * kW1, offW2l = 2 * kW1 + kW2;
     static constexpr int offA = 2 * kW1 + 2 * kW2;           // [2 stages][hi | lo]
     static constexpr int offH = offA + 2 * 2 * kATile;       // hidden tile [hi | lo]
     static constexpr int offF = offH + 2 * kATile;           // [2 stages] fp32
-    static constexpr int offBias = offF + 2 * kFTile;        // b1, b2
+    static constexpr int offBias = offF + kFS * kFTile;      // b1, b2
     static constexpr int offBar = offBias + 2 * C * 4;
     static constexpr int smem = offBar + 256;
     static constexpr int tmem_cols = 4 * C;                  // acc1[2], acc2[2]: 256 / 128 columns
@@ -103,23 +116,25 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)); }
 
 template <int C>
-__global__ void __launch_bounds__(kThreadsT5, 1)
+__global__ void __launch_bounds__(32 * (2 + 4 * T5Groups<C>::value + 4), 1)
 resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, float* __restrict__ out,
                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                    const float* __restrict__ b2, long long T, int dil, float rs, int tiles_per_clip, int total_tiles) {
     using L = T5<C>;
+    constexpr int kGroups = T5Groups<C>::value, kThreadsT5 = 32 * (2 + 4 * kGroups + 4);
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::offBar);
-    uint64_t *f_full = bars, *f_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *acc1_full = bars + 8,
-             *acc1_empty = bars + 10, *acc2_full = bars + 12, *acc2_empty = bars + 14, *h_full = bars + 16, *h_empty = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t *f_full = bars, *f_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *acc1_full = bars + 12,
+             *acc1_empty = bars + 14, *acc2_full = bars + 16, *acc2_empty = bars + 18, *h_full = bars + 20, *h_empty = bars + 21;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    constexpr int FS = L::kFS;
     float* bias = reinterpret_cast<float*>(sm + L::offBias);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- once per CTA: barriers, TMEM, weights (scaled, split, swizzled), biases ------------------------------------
     if (tid == 0) {
+        for (int i = 0; i < FS; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 128); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 128);
             mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
             mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 128);
             mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 128);
@@ -165,12 +180,28 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            // the rows of the tiles this CTA takes next are pulled into L2 two iterations ahead (every row is read three times,
+            // as the centre tap of one tile and the side taps of two others: whoever comes first pays the HBM latency), so
+            // that the ring's loads are L2 hits - two stages of 32 KB cannot cover an HBM round trip
+            auto prefetch = [&](int tile) {
+                if (tile >= total_tiles) return;
+                const int nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * kBM;
+                for (int tap = 0; tap < 3; ++tap)
+                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&map_x)), "r"(0), "r"(t0 + (tap - 1) * dil), "r"(nb) : "memory");
+            };
+#if JK_T5_PREFETCH
+            prefetch(first + stride);
+#endif
             uint32_t kt = 0;
             for (int tile = first; tile < total_tiles; tile += stride) {
                 const int nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * kBM;
+#if JK_T5_PREFETCH
+                prefetch(tile + 2 * stride);
+#endif
                 for (int tap = 0; tap < 3; ++tap, ++kt) {
-                    const int s = kt & 1;
-                    mbar_wait(&f_empty[s], ((kt >> 1) & 1) ^ 1);
+                    const int s = kt % FS;
+                    mbar_wait(&f_empty[s], ((kt / FS) & 1) ^ 1);
                     mbar_expect_tx(&f_full[s], (uint32_t)L::kFTile);
                     tma_load_3d(sm + L::offF + s * L::kFTile, &map_x, 0, t0 + (tap - 1) * dil, nb, &f_full[s]);
                 }
@@ -222,40 +253,52 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             }
             if (it > 0) conv2(it - 1);
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + 4 * kGroups) {
         // ================= converters: fp32 tap tile -> relu -> hi / lo planes =================
-        const int ct = tid - 64;                          // 0..127
+        // kGroups groups of 128 threads; with two groups, group g takes the taps whose counter is g mod 2 - that is the
+        // operand slot g and the fp32 slots g (mod 2) - so two taps are converted concurrently and every barrier still
+        // sees exactly the 128 arrivals of one group per use
+        const int cg = (warp - 2) >> 2;
+        const int ct = (tid - 64) & 127;                  // 0..127 inside the group
         constexpr int CH = C / 4;                         // float4 chunks per row
         constexpr int PER = kBM * CH / 128;               // items per thread
         uint32_t kt = 0;
         for (int tile = first; tile < total_tiles; tile += stride) {
             for (int tap = 0; tap < 3; ++tap, ++kt) {
-                const int s = kt & 1;
-                mbar_wait(&f_full[s], (kt >> 1) & 1);
-                const float4* f = reinterpret_cast<const float4*>(sm + L::offF + s * L::kFTile);
+                if (kGroups == 2 && (int)(kt & 1) != cg) continue;
+                const int s = kt & 1, fs = kt % FS;
+                mbar_wait(&f_full[fs], (kt / FS) & 1);
+                const float4* f = reinterpret_cast<const float4*>(sm + L::offF + fs * L::kFTile);
                 float4 v[PER];
 #pragma unroll
                 for (int j = 0; j < PER; ++j) v[j] = f[ct + j * 128];
-                mbar_arrive(&f_empty[s]);                 // the values are in registers: the fp32 slot may be refilled
+                uint2 h[PER], l[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    t5_split2(fmaxf(v[j].x, 0.f), fmaxf(v[j].y, 0.f), h[j].x, l[j].x);
+                    t5_split2(fmaxf(v[j].z, 0.f), fmaxf(v[j].w, 0.f), h[j].y, l[j].y);
+                }
                 mbar_wait(&a_empty[s], ((kt >> 1) & 1) ^ 1);
                 uint8_t* ah = sm + L::offA + s * 2 * L::kATile;
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
                     const int item = ct + j * 128, r = item / CH, c4 = item % CH;
-                    uint2 h, l;
-                    t5_split2(fmaxf(v[j].x, 0.f), fmaxf(v[j].y, 0.f), h.x, l.x);
-                    t5_split2(fmaxf(v[j].z, 0.f), fmaxf(v[j].w, 0.f), h.y, l.y);
                     const uint32_t o = sw_off(r, c4 >> 1) + (c4 & 1) * 8;
-                    *reinterpret_cast<uint2*>(ah + o) = h;
-                    *reinterpret_cast<uint2*>(ah + L::kATile + o) = l;
+                    *reinterpret_cast<uint2*>(ah + o) = h[j];
+                    *reinterpret_cast<uint2*>(ah + L::kATile + o) = l[j];
                 }
+                // The fp32 slot is released only here: every loaded value has been consumed by the stores above (an arrive
+                // issued right behind the loads let TMA refill the slot under them - tools/t5_check.py showed O(1) errors in
+                // single 2-row LDS.128 groups), and the proxy fence below also orders this thread's generic reads of the slot
+                // before the async-proxy writes of the refill.
                 fence_async_smem();
                 mbar_arrive(&a_full[s]);
+                mbar_arrive(&f_empty[fs]);
             }
         }
     } else {
         // ================= epilogues =================
-        const int q = warp & 3, row = q * 32 + lane;      // TMEM lane quarter of this warp; row of the tile
+        const int q = warp & 3, row = q * 32 + lane;      // TMEM lane quarter of this warp (warp id mod 4); row of the tile
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t* hh = sm + L::offH;
         uint32_t it = 0;
@@ -272,10 +315,14 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
                 t5_ld32(lane_base + p * C + c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const float a = fmaxf(fmaf(__uint_as_float(r[e]), kWInvT5, bias[c0 + e]), 0.f);
-                    const float b = fmaxf(fmaf(__uint_as_float(r[e + 1]), kWInvT5, bias[c0 + e + 1]), 0.f);
-                    t5_split2(a, b, hi[(c0 + e) >> 1], lo[(c0 + e) >> 1]);
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + e);      // one broadcast LDS.128 per 4 columns
+                    const float a0 = fmaxf(fmaf(__uint_as_float(r[e]), kWInvT5, bb.x), 0.f);
+                    const float a1 = fmaxf(fmaf(__uint_as_float(r[e + 1]), kWInvT5, bb.y), 0.f);
+                    const float a2 = fmaxf(fmaf(__uint_as_float(r[e + 2]), kWInvT5, bb.z), 0.f);
+                    const float a3 = fmaxf(fmaf(__uint_as_float(r[e + 3]), kWInvT5, bb.w), 0.f);
+                    t5_split2(a0, a1, hi[(c0 + e) >> 1], lo[(c0 + e) >> 1]);
+                    t5_split2(a2, a3, hi[((c0 + e) >> 1) + 1], lo[((c0 + e) >> 1) + 1]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -290,30 +337,49 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             fence_async_smem();
             mbar_arrive(h_full);
             // ---- (2) out = x + res_scale * (conv2 / 2^8 + b2) ---------------------------------------------------
+            // TMEM hands a thread one ROW of the tile; row-per-lane 16-byte global accesses touch 32 different lines per
+            // instruction and saturated the L1 tag stage (ncu: l1tex 80 % of peak, profiles/ncu_resblock_t5_r02a.txt).
+            // So the tile goes through shared memory: res_scale * (acc / 2^8 + b2) row by row into the hidden-tile region
+            // (free between the k1 conv that just read it and the next tile's hidden tile), then all 128 threads add the
+            // residual and store with consecutive lanes on consecutive 16-byte chunks.
             mbar_wait(&acc2_full[p], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long t = (long long)t0 + row;
-            const size_t gro = ((size_t)nb * T + t) * C;
+            float* stage = reinterpret_cast<float*>(sm + L::offH);      // [128][C] fp32, 16-byte chunks XOR-swizzled with row & 7
 #pragma unroll
             for (int c0 = 0; c0 < C; c0 += 32) {
                 uint32_t r[32];
                 t5_ld32(lane_base + 2 * C + p * C + c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (t < T) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        const float4 xr = __ldg(reinterpret_cast<const float4*>(x + gro + c0 + e));
-                        float4 o;
-                        o.x = rs * fmaf(__uint_as_float(r[e]), kWInvT5, bias[C + c0 + e]); o.x += xr.x;
-                        o.y = rs * fmaf(__uint_as_float(r[e + 1]), kWInvT5, bias[C + c0 + e + 1]); o.y += xr.y;
-                        o.z = rs * fmaf(__uint_as_float(r[e + 2]), kWInvT5, bias[C + c0 + e + 2]); o.z += xr.z;
-                        o.w = rs * fmaf(__uint_as_float(r[e + 3]), kWInvT5, bias[C + c0 + e + 3]); o.w += xr.w;
-                        *reinterpret_cast<float4*>(out + gro + c0 + e) = o;
-                    }
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bias + C + c0 + e);
+                    float4 o;
+                    o.x = rs * fmaf(__uint_as_float(r[e]), kWInvT5, bb.x);
+                    o.y = rs * fmaf(__uint_as_float(r[e + 1]), kWInvT5, bb.y);
+                    o.z = rs * fmaf(__uint_as_float(r[e + 2]), kWInvT5, bb.z);
+                    o.w = rs * fmaf(__uint_as_float(r[e + 3]), kWInvT5, bb.w);
+                    *reinterpret_cast<float4*>(stage + row * C + ((((c0 + e) >> 2) ^ (row & 7)) << 2)) = o;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc2_empty[p]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                constexpr int CH4 = C / 4;
+                const int et = tid - 32 * (2 + 4 * kGroups);      // 0..127
+                const float* xin = x + ((size_t)nb * T + t0) * C;
+                float* xo = out + ((size_t)nb * T + t0) * C;
+#pragma unroll 4
+                for (int i = 0; i < CH4; ++i) {
+                    const int item = et + i * 128, rr = item / CH4, jj = item % CH4;
+                    if ((long long)t0 + rr < T) {
+                        const float4 v = *reinterpret_cast<const float4*>(stage + rr * C + ((jj ^ (rr & 7)) << 2));
+                        const float4 xr = __ldg(reinterpret_cast<const float4*>(xin) + item);
+                        *(reinterpret_cast<float4*>(xo) + item) = make_float4(v.x + xr.x, v.y + xr.y, v.z + xr.z, v.w + xr.w);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the region becomes the next tile's hidden tile
         }
     }
     __syncthreads();
@@ -364,7 +430,7 @@ int launch_t5(const float* x, float* out, const float* w1, const float* b1, cons
     const long long per_clip = (T + kBM - 1) / kBM, total = per_clip * n;
     JK_REQUIRE(total < (1ll << 31) && T + 4096 < (1ll << 31), "clip too long for 32-bit tile coordinates");
     const unsigned grid = (unsigned)std::min<long long>(total, sms[dev & 63]);
-    resblock_t5_kernel<C><<<grid, kThreadsT5, T5<C>::smem, stream>>>(map, x, out, w1, b1, w2, b2, T, dil, rs, (int)per_clip, (int)total);
+    resblock_t5_kernel<C><<<grid, 32 * (2 + 4 * T5Groups<C>::value + 4), T5<C>::smem, stream>>>(map, x, out, w1, b1, w2, b2, T, dil, rs, (int)per_clip, (int)total);
     JK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

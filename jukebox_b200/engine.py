@@ -114,6 +114,13 @@ class DecodeEngine:
 
     # ---- chunked prefill ---------------------------------------------------------------
     @property
+    def has_logits_gemm(self):
+        """True if the logits run as a Conv1D on the tensor cores (then `step(logit_bias=...)` is worth computing)"""
+        out = C.c_int(0)
+        check(lib().jk_prior_has_logits_gemm(self.handle, C.byref(out)))
+        return bool(out.value)
+
+    @property
     def prefill_capacity(self):
         """positions one `prefill` call can take (0: this configuration steps its given tokens)"""
         out = C.c_int(0)
@@ -137,7 +144,7 @@ class DecodeEngine:
 
     # ---- one token -----------------------------------------------------------------------
     def step(self, n, *, x_in=None, tokens=None, y_cond=None, x_cond=None, h_out=None, logits=None,
-             logits_tstride=0):
+             logits_tstride=0, logit_bias=None):
         a = _lib.StepArgs()
         a.n_samples = n
         a.x_in = ptr(x_in)
@@ -151,6 +158,10 @@ class DecodeEngine:
         if logits is not None:
             a.logits_bstride = logits.stride(0)
             a.logits_tstride = logits_tstride
+        a.logit_bias = ptr(logit_bias)
+        if logit_bias is not None:        # [n, 1 or n_ctx, bins] fp32: x_cond . x_out^T of every position (jkb200.h)
+            a.logit_bias_bstride = logit_bias.stride(0)
+            a.logit_bias_tstride = logit_bias.stride(1) if logit_bias.shape[1] > 1 else 0
         with torch.cuda.device(self.device):
             check(lib().jk_prior_step(self.handle, C.byref(a), stream_ptr()))
         self.position += 1

@@ -255,6 +255,15 @@ class SamplingWindow:
         self.seed = int(t.empty((), dtype=t.int64).random_().item())
         self.pos = 0
         self.fbuf = None
+        # x_cond is added BEHIND the stack (autoregressive.py:226-227) and the logits are linear in the activation:
+        # x_cond . x_out^T of every position is computed once per window, so that the engine's logits product can take
+        # the fp16-valued h on the tensor cores and add this bias in its epilogue (jkb200.h: jk_step_args.logit_bias)
+        self.logit_bias = None
+        if ca.add_cond_after_transformer and self.x_cond is not None and eng.has_logits_gemm:
+            from ..transformer import f32
+            with t.no_grad():
+                Lc = self.x_cond.shape[1]
+                self.logit_bias = f32.linear_nk(self.x_cond.reshape(N * Lc, ca.width), ca.x_out.weight).view(N, Lc, ca.bins)
         with t.no_grad():
             if 1 < P <= eng.prefill_capacity:
                 # the given tokens go through all layers at once (the reference's chunked primed_sample,
@@ -279,7 +288,7 @@ class SamplingWindow:
             for sample_t in get_range(range(self.pos, upto)):
                 need = self.get_preds or sample_t >= P
                 eng.step(N, tokens=tokens, y_cond=self.y_cond, x_cond=self.x_cond,
-                         logits=self.lbuf if need else None, logits_tstride=self.tstride)
+                         logits=self.lbuf if need else None, logits_tstride=self.tstride, logit_bias=self.logit_bias)
                 if sample_t >= P:
                     x = self.preds[:, sample_t] if self.get_preds else self.lbuf
                     if self.top_k or self.top_p:   # x / temp -> top-k / nucleus filter (ops.py:113-142): one launch

@@ -105,6 +105,27 @@ def test_prefill_against_oracle_and_public_api():
     assert z1.shape == (n, P + 8) and torch.equal(z1[:, :P], tokens[:, :P])
 
 
+@pytest.mark.parametrize("bins", [77, 2127 % 256 + 8])
+def test_logits_gemm_with_ragged_bins_against_oracle(bins):
+    """the logits Conv1D (hi / lo fp16 split of the fp32 x_out on the tensor cores, decode_engine.cu) with a vocabulary
+    that is not a multiple of the 8-column MMA group (1b_lyrics: 2127 = 2048 + 79): the last group is padded with zero
+    weights and its padding columns are never stored; logits against the oracle's fp32 product"""
+    from oracle.transformer_np import PriorOracle
+    order, width, depth, heads, n_ctx, blocks = 2, 256, 3, 2, 64, 4
+    m, w = _model(order, width, depth, heads, n_ctx, blocks, None, bins=bins, seed=bins)
+    n, P, K = 5, 9, 4
+    g = torch.Generator().manual_seed(bins)
+    tokens = torch.randint(0, m.bins, (n, n_ctx), generator=g).cuda()
+    yc = torch.randn(n, width, generator=g).cuda()
+    got = _run(m, n, tokens, P, K, yc, None, use_prefill=False)
+    orc = PriorOracle(w, n_ctx, m.bins, width, depth, heads, attn_order=order, blocks=blocks, x_cond=False, y_cond=True)
+    ref = orc.logits(tokens.cpu().numpy(), None, yc.cpu().numpy()[:, None, :], None, True, n_steps=P + K)
+    assert got.shape[-1] == bins and np.isfinite(got).all()
+    e = rel_err(got, ref[:, P:P + K])
+    print(f"bins {bins}: logits vs oracle fp16 {e:.2e}")
+    assert e < 5e-3
+
+
 def test_only_encode_forward_uses_prefill():
     """forward() of an only_encode stack (the lyric encoder of separated priors): prefill h_out vs stepping"""
     from jukebox_b200.prior.autoregressive import ConditionalAutoregressive2D

@@ -34,6 +34,10 @@ def main():
     lbuf = torch.empty(n, ca.bins, device="cuda")
     yc = torch.randn(n, ca.width, device="cuda") if ca.y_cond else None
     xc = torch.zeros(n, 1, ca.width, device="cuda") if ca.x_cond else None
+    lb = None       # x_cond . x_out^T (SamplingWindow computes it once per window for the tensor-core logits product)
+    if xc is not None and ca.add_cond_after_transformer and os.environ.get("JK_LOGIT_BIAS", "1") != "0":
+        from jukebox_b200.transformer import f32 as _f32
+        lb = _f32.linear_nk(xc.reshape(n, ca.width), ca.x_out.weight).view(n, 1, ca.bins) if hasattr(ca, "x_out") else None
     if ca.transformer.encoder_dims:
         eng.set_encoder_kv(torch.randn(n, ca.transformer.encoder_dims, ca.width, device="cuda"))
     depth = ca.transformer.n_depth
@@ -42,7 +46,7 @@ def main():
     eng.reset(pos)
     rows = []
     for i in range(6):
-        eng.step(n, tokens=toks, y_cond=yc, x_cond=xc, logits=lbuf)
+        eng.step(n, tokens=toks, y_cond=yc, x_cond=xc, logits=lbuf, logit_bias=lb)
         torch.cuda.synchronize()
         prof = eng.debug_buffer(5).view(torch.int64).cpu().numpy()
         stamps = prof[: 2 + 5 * depth + 1].astype(np.float64)
