@@ -955,14 +955,29 @@ __global__ void __launch_bounds__(256) conv1d_cl_narrow_kernel(ConvP P, int span
         const long long off = span >= 0 ? min_off : (pass == 0 ? P.tap_off[0] : pass == 1 ? P.tap_off[1] : pass == 2 ? P.tap_off[2] : P.tap_off[3]);
         const int rows = span >= 0 ? 256 + span : 256;
         const int c4sh = (c4n & (c4n - 1)) == 0 ? 31 - __clz(c4n) : -1;      // c_in = 32 / 64: shifts, not a division per chunk
+        if (!P.relu_in) {
+            // cp.async (LDGSTS): every 16-byte chunk of the window is requested at once, nothing passes through registers -
+            // the staging costs one memory round trip instead of a chain of load -> store batches; rows outside the clip are
+            // zero-filled by the src-size operand
+            for (int i = threadIdx.x; i < rows * c4n; i += 256) {
+                const int r = c4sh >= 0 ? (i >> c4sh) : i / c4n, c4 = i - r * c4n;
+                const long long tp = span >= 0 ? t0 + r + off : (t0 + r) * P.in_stride + off;
+                const bool ok = tp >= 0 && tp < P.t_in;
+                const float4* src = reinterpret_cast<const float4*>(in + (size_t)(ok ? tp : 0) * CI) + c4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xs + (size_t)r * XS + c4 * 4)),
+                             "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        } else {
 #pragma unroll 4
-        for (int i = threadIdx.x; i < rows * c4n; i += 256) {
-            const int r = c4sh >= 0 ? (i >> c4sh) : i / c4n, c4 = i - r * c4n;
-            const long long tp = span >= 0 ? t0 + r + off : (t0 + r) * P.in_stride + off;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp >= 0 && tp < P.t_in) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)tp * CI) + c4);
-            if (P.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<float4*>(xs + (size_t)r * XS + c4 * 4) = v;
+            for (int i = threadIdx.x; i < rows * c4n; i += 256) {
+                const int r = c4sh >= 0 ? (i >> c4sh) : i / c4n, c4 = i - r * c4n;
+                const long long tp = span >= 0 ? t0 + r + off : (t0 + r) * P.in_stride + off;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tp >= 0 && tp < P.t_in) v = __ldg(reinterpret_cast<const float4*>(in + (size_t)tp * CI) + c4);
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                *reinterpret_cast<float4*>(xs + (size_t)r * XS + c4 * 4) = v;
+            }
         }
         __syncthreads();
         const int tap_lo = span >= 0 ? 0 : pass, tap_hi = span >= 0 ? P.n_taps : pass + 1;
@@ -1082,6 +1097,14 @@ extern "C" int jk_vq_gather(const int64_t* idx, const float* codebook, float* ou
     return 0;
 }
 
+namespace jk {
+int conv_t5(const float* in, long long t_in, int c_in, float* out, long long t_out, int c_out, const float* w, const float* bias,
+            const float* res, int n_taps, const int* tap_off, int out_stride, int out_offset, int relu_in, float scale, int n,
+            cudaStream_t stream);                                                 // vqvae_t5.cu
+int resblock_t5(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2, int n,
+                long long T, int C, int dil, float rs, cudaStream_t stream);      // vqvae_t5.cu
+}
+
 extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     JK_REQUIRE(a && a->in && a->out && a->w, "null argument");
@@ -1117,6 +1140,11 @@ extern "C" int jk_conv1d_cl(const jk_conv_args* a, jk_stream_t stream_) {
     static const bool conv_exact = getenv("JK_CONV_EXACT") != nullptr;      // A/B: keep the FMA tile kernel for flagged convs
     if (a->tensor_cores && !conv_exact && (a->c_in == 32 || a->c_in == 64) && (a->c_out == 32 || a->c_out == 64) &&
         (((uintptr_t)a->in | (uintptr_t)a->out | (uintptr_t)a->bias | (uintptr_t)a->res) & 15) == 0) {
+        // tcgen05 + TMA tap-GEMM (vqvae_t5.cu) for stride-1 inputs of >= 128 positions; JK_CONV_T5=0 keeps the mma.sync kernel
+        static const bool t5 = !(getenv("JK_CONV_T5") && atoi(getenv("JK_CONV_T5")) == 0);
+        if (t5 && a->in_stride == 1 && a->n_taps <= 3 && a->t_in >= 128 && a->t_out >= 1)
+            return jk::conv_t5(a->in, a->t_in, a->c_in, a->out, a->t_out, a->c_out, a->w, a->bias, a->res, a->n_taps, a->tap_off,
+                               a->out_stride, a->out_offset, a->relu_in, a->scale, a->n, stream);
         if (a->c_in == 64 && a->c_out == 64) return launch_conv_h2<64, 64>(P, a->n, stream);
         if (a->c_in == 64 && a->c_out == 32) return launch_conv_h2<64, 32>(P, a->n, stream);
         if (a->c_in == 32 && a->c_out == 64) return launch_conv_h2<32, 64>(P, a->n, stream);
@@ -1157,10 +1185,6 @@ extern "C" int jk_resblock_cl(const float* x, float* out, float* tmp, const floa
     return jk_conv1d_cl(&a, stream);
 }
 
-namespace jk {
-int resblock_t5(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2, int n,
-                long long T, int C, int dil, float rs, cudaStream_t stream);      // vqvae_t5.cu
-}
 
 extern "C" int jk_resblock_tc(const float* x, float* out, const float* w1, const float* b1, const float* w2, const float* b2,
                               int n, int64_t T, int C, int dilation, float res_scale, jk_stream_t stream) {

@@ -389,6 +389,216 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tap-GEMM convolution on the same machinery, for the decoder-side convs BETWEEN the residual blocks (the k3 input conv of
+// a DecoderConvBock, the two 2-tap phases of its k4-s2 transposed convs; encdec.py:28-46):
+//   out[t * os + oo, :] = res + scale * (sum_j x[t + off_j, :] . W_j + b),   c_in, c_out in {32, 64}, <= 3 taps, stride-1 input.
+// Roles as in resblock_t5_kernel minus the hidden tile: TMA producer (one tap tile per load), 4 converter warps, MMA issuer
+// (double-buffered accumulator of CO columns), 4 epilogue warps that stage scale * (acc / 2^8 + b) through shared memory and
+// then add the residual / store whole rows with consecutive lanes on consecutive 16-byte chunks.
+// ---------------------------------------------------------------------------------------
+struct ConvT5P {
+    const float* in; float* out; const float* w; const float* bias; const float* res;
+    long long t_in, t_out;
+    int n_taps, tap_off[3], out_stride, out_offset, relu_in;
+    float scale;
+};
+
+template <int CI, int CO>
+struct T5C {
+    static constexpr int kWBlock = CO * 128;                 // one tap of a weight plane: CO rows x 128 bytes (K = CI <= 64)
+    static constexpr int kW = 3 * kWBlock;                   // bytes per plane (<= 3 taps)
+    static constexpr int kATile = kBM * 128;
+    static constexpr int kFTile = kBM * CI * 4;
+    static constexpr int kFS = CI == 64 ? 2 : 4;
+    static constexpr int offWh = 0, offWl = kW;
+    static constexpr int offA = 2 * kW;                      // [2 stages][hi | lo]
+    static constexpr int offS = offA + 2 * 2 * kATile;       // output staging [128][CO] fp32
+    static constexpr int offF = offS + kBM * CO * 4;
+    static constexpr int offBias = offF + kFS * kFTile;
+    static constexpr int offBar = offBias + CO * 4;
+    static constexpr int smem = offBar + 256;
+    static constexpr int tmem_cols = 2 * CO < 32 ? 32 : 2 * CO;     // 64 or 128: a power of two >= 32
+};
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(320, 1)
+conv_t5_kernel(const __grid_constant__ CUtensorMap map_x, ConvT5P P, int tiles_per_clip, int total_tiles) {
+    using L = T5C<CI, CO>;
+    constexpr int FS = L::kFS;
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::offBar);
+    uint64_t *f_full = bars, *f_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *acc_full = bars + 12,
+             *acc_empty = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* bias = reinterpret_cast<float*>(sm + L::offBias);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntap = P.n_taps;
+    if (tid == 0) {
+        for (int i = 0; i < FS; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128);
+        }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(L::tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int i = tid; i < ntap * CI * CO; i += 320) {         // w[(tap * CI + ci) * CO + co] -> B[tap][row co][k ci]
+        const int tap = i / (CI * CO), ci = (i / CO) % CI, co = i % CO;
+        unsigned short h, l;
+        const float v = kWScaleT5 * __ldg(P.w + i);
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        const float rem = v - __half2float(__ushort_as_half(h));
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(rem));
+        const uint32_t o = tap * L::kWBlock + sw_off(co, ci >> 3) + (ci & 7) * 2;
+        *reinterpret_cast<unsigned short*>(sm + L::offWh + o) = h;
+        *reinterpret_cast<unsigned short*>(sm + L::offWl + o) = l;
+    }
+    for (int i = tid; i < CO; i += 320) bias[i] = P.bias ? __ldg(P.bias + i) : 0.f;
+    fence_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int first = blockIdx.x, stride = gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t kt = 0;
+            for (int tile = first; tile < total_tiles; tile += stride) {
+                const int nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * kBM;
+                for (int tap = 0; tap < ntap; ++tap, ++kt) {
+                    const int s = kt % FS;
+                    mbar_wait(&f_empty[s], ((kt / FS) & 1) ^ 1);
+                    mbar_expect_tx(&f_full[s], (uint32_t)L::kFTile);
+                    const int off = tap == 0 ? P.tap_off[0] : tap == 1 ? P.tap_off[1] : P.tap_off[2];     // no local copy of the array
+                    tma_load_3d(sm + L::offF + s * L::kFTile, &map_x, 0, t0 + off, nb, &f_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            const uint32_t wh = smem_u32(sm + L::offWh), wl = smem_u32(sm + L::offWl);
+            uint32_t kt = 0, it = 0;
+            for (int tile = first; tile < total_tiles; tile += stride, ++it) {
+                const uint32_t p = it & 1;
+                mbar_wait(&acc_empty[p], ((it >> 1) & 1) ^ 1);
+                const uint32_t d = tmem_base + p * CO;
+                for (int tap = 0; tap < ntap; ++tap, ++kt) {
+                    const int s = kt & 1;
+                    mbar_wait(&a_full[s], (kt >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ah = smem_u32(sm + L::offA + s * 2 * L::kATile), al = ah + L::kATile;
+                    const uint32_t bh = wh + tap * L::kWBlock, bl = wl + tap * L::kWBlock;
+#pragma unroll
+                    for (int k = 0; k < CI / 16; ++k) {
+                        t5_mma(d, t5_desc(al + k * 32), t5_desc(bh + k * 32), idesc, (tap | k) ? 1u : 0u);
+                        t5_mma(d, t5_desc(ah + k * 32), t5_desc(bl + k * 32), idesc, 1u);
+                        t5_mma(d, t5_desc(ah + k * 32), t5_desc(bh + k * 32), idesc, 1u);
+                    }
+                    t5_commit(&a_empty[s]);
+                }
+                t5_commit(&acc_full[p]);
+            }
+        }
+    } else if (warp < 6) {
+        const int ct = tid - 64;
+        constexpr int CH = CI / 4, PER = kBM * CH / 128;
+        const bool relu = P.relu_in != 0;
+        uint32_t kt = 0;
+        for (int tile = first; tile < total_tiles; tile += stride) {
+            for (int tap = 0; tap < ntap; ++tap, ++kt) {
+                const int s = kt & 1, fs = kt % FS;
+                mbar_wait(&f_full[fs], (kt / FS) & 1);
+                const float4* f = reinterpret_cast<const float4*>(sm + L::offF + fs * L::kFTile);
+                float4 v[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) v[j] = f[ct + j * 128];
+                uint2 h[PER], l[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    if (relu) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+                    t5_split2(v[j].x, v[j].y, h[j].x, l[j].x);
+                    t5_split2(v[j].z, v[j].w, h[j].y, l[j].y);
+                }
+                mbar_wait(&a_empty[s], ((kt >> 1) & 1) ^ 1);
+                uint8_t* ah = sm + L::offA + s * 2 * L::kATile;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int item = ct + j * 128, r = item / CH, c4 = item % CH;
+                    const uint32_t o = sw_off(r, c4 >> 1) + (c4 & 1) * 8;
+                    *reinterpret_cast<uint2*>(ah + o) = h[j];
+                    *reinterpret_cast<uint2*>(ah + L::kATile + o) = l[j];
+                }
+                fence_async_smem();
+                mbar_arrive(&a_full[s]);
+                mbar_arrive(&f_empty[fs]);          // only now: the loaded values have been consumed (see resblock_t5_kernel)
+            }
+        }
+    } else {
+        const int q = warp & 3, row = q * 32 + lane, et = tid - 192;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* stage = reinterpret_cast<float*>(sm + L::offS);
+        const long long rows_out = P.t_out * P.out_stride;
+        uint32_t it = 0;
+        for (int tile = first; tile < total_tiles; tile += stride, ++it) {
+            const uint32_t p = it & 1;
+            const int nb = tile / tiles_per_clip, t0 = (tile - nb * tiles_per_clip) * kBM;
+            mbar_wait(&acc_full[p], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < CO; c0 += 32) {
+                uint32_t r[32];
+                t5_ld32(lane_base + p * CO + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + e);
+                    float4 o;
+                    o.x = P.scale * fmaf(__uint_as_float(r[e]), kWInvT5, bb.x);
+                    o.y = P.scale * fmaf(__uint_as_float(r[e + 1]), kWInvT5, bb.y);
+                    o.z = P.scale * fmaf(__uint_as_float(r[e + 2]), kWInvT5, bb.z);
+                    o.w = P.scale * fmaf(__uint_as_float(r[e + 3]), kWInvT5, bb.w);
+                    *reinterpret_cast<float4*>(stage + row * CO + ((((c0 + e) >> 2) ^ (row & 7)) << 2)) = o;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[p]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                constexpr int CH4 = CO / 4;
+                float* ob = P.out + (size_t)nb * rows_out * CO;
+                const float* rb = P.res ? P.res + (size_t)nb * rows_out * CO : nullptr;
+#pragma unroll 4
+                for (int i = 0; i < CH4; ++i) {
+                    const int item = et + i * 128, rr = item / CH4, jj = item % CH4;
+                    const long long t = (long long)t0 + rr;
+                    if (t < P.t_out) {
+                        float4 v = *reinterpret_cast<const float4*>(stage + rr * CO + ((jj ^ (rr & 7)) << 2));
+                        const size_t o = (size_t)(t * P.out_stride + P.out_offset) * CO + jj * 4;
+                        if (rb) {
+                            const float4 xr = __ldg(reinterpret_cast<const float4*>(rb + o));
+                            v.x += xr.x; v.y += xr.y; v.z += xr.z; v.w += xr.w;
+                        }
+                        *reinterpret_cast<float4*>(ob + o) = v;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::tmem_cols));
+    }
+}
+
 typedef CUresult (*EncodeTiledFnT5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -435,6 +645,36 @@ int launch_t5(const float* x, float* out, const float* w1, const float* b1, cons
     return 0;
 }
 
+
+template <int CI, int CO>
+int launch_conv_t5(const ConvT5P& P, int n, cudaStream_t stream) {
+    EncodeTiledFnT5 enc = t5_encode();
+    JK_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap map;
+    cuuint64_t dims[3] = {(cuuint64_t)CI, (cuuint64_t)P.t_in, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)CI * 4, (cuuint64_t)P.t_in * CI * 4};
+    cuuint32_t box[3] = {(cuuint32_t)CI, (cuuint32_t)kBM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    JK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for a [%d, %lld, %d] fp32 tensor", (int)r, n, P.t_in, CI);
+    static bool attr_set[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    JK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        JK_CHECK_CUDA(cudaFuncSetAttribute((conv_t5_kernel<CI, CO>), cudaFuncAttributeMaxDynamicSharedMemorySize, T5C<CI, CO>::smem));
+        JK_CHECK_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+        attr_set[dev & 63] = true;
+    }
+    const long long per_clip = (P.t_out + kBM - 1) / kBM, total = per_clip * n;
+    JK_REQUIRE(total < (1ll << 31) && P.t_in + 4096 < (1ll << 31), "clip too long for 32-bit tile coordinates");
+    const unsigned grid = (unsigned)std::min<long long>(total, sms[dev & 63]);
+    conv_t5_kernel<CI, CO><<<grid, 320, T5C<CI, CO>::smem, stream>>>(map, P, (int)per_clip, (int)total);
+    JK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 }  // namespace
 
 namespace jk {
@@ -444,6 +684,21 @@ int resblock_t5(const float* x, float* out, const float* w1, const float* b1, co
     if (C == 64) return launch_t5<64>(x, out, w1, b1, w2, b2, n, T, dil, rs, stream);
     if (C == 32) return launch_t5<32>(x, out, w1, b1, w2, b2, n, T, dil, rs, stream);
     JK_REQUIRE(false, "resblock_t5: C must be 32 or 64 (got %d)", C);
+    return 0;
+}
+// jk_conv1d_cl with tensor_cores = 1 dispatches here: stride-1 input, <= 3 taps, c_in / c_out in {32, 64}, t_in >= 128
+int conv_t5(const float* in, long long t_in, int c_in, float* out, long long t_out, int c_out, const float* w, const float* bias,
+            const float* res, int n_taps, const int* tap_off, int out_stride, int out_offset, int relu_in, float scale, int n,
+            cudaStream_t stream) {
+    ConvT5P P;
+    P.in = in; P.out = out; P.w = w; P.bias = bias; P.res = res; P.t_in = t_in; P.t_out = t_out; P.n_taps = n_taps;
+    for (int i = 0; i < 3; ++i) P.tap_off[i] = i < n_taps ? tap_off[i] : 0;
+    P.out_stride = out_stride; P.out_offset = out_offset; P.relu_in = relu_in; P.scale = scale;
+    if (c_in == 64 && c_out == 64) return launch_conv_t5<64, 64>(P, n, stream);
+    if (c_in == 64 && c_out == 32) return launch_conv_t5<64, 32>(P, n, stream);
+    if (c_in == 32 && c_out == 64) return launch_conv_t5<32, 64>(P, n, stream);
+    if (c_in == 32 && c_out == 32) return launch_conv_t5<32, 32>(P, n, stream);
+    JK_REQUIRE(false, "conv_t5: channels must be 32 or 64 (got %d -> %d)", c_in, c_out);
     return 0;
 }
 }  // namespace jk

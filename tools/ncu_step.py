@@ -26,8 +26,12 @@ toks = torch.randint(0, ca.bins, (n, L), device="cuda")
 lbuf = torch.empty(n, ca.bins, device="cuda")
 yc = torch.randn(n, ca.width, device="cuda")
 xc = torch.zeros(n, 1, ca.width, device="cuda")
+lb = None       # x_cond . x_out^T: the logit bias SamplingWindow computes once per window (tensor-core logits product)
+if ca.add_cond_after_transformer and eng.has_logits_gemm:
+    from jukebox_b200.transformer import f32 as _f32
+    lb = _f32.linear_nk(xc.reshape(n, ca.width), ca.x_out.weight).view(n, 1, ca.bins)
 eng.reset(min(args.pos, L - args.steps - 1))
 for _ in range(args.steps):
-    eng.step(n, tokens=toks, y_cond=yc, x_cond=xc, logits=lbuf)
+    eng.step(n, tokens=toks, y_cond=yc, x_cond=xc, logits=lbuf, logit_bias=lb)
 torch.cuda.synchronize()
 print("done", eng.position)
