@@ -493,11 +493,17 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, int epi_, int l, int p
     // arrival on a foreign slot's empty barrier always belongs to the barrier's current pass); a phase longer than the ring
     // (5b_lyrics: 38 slots, 6 in the ring) keeps every warp in the producer's order.  An already-complete try_wait costs
     // ~90 cycles: three of them per warp per phase were pure overhead.
-    const bool in_order = !JK_SKIP_FOREIGN_WAIT || ((nkk + kpc - 1) >> (31 - __clz(kpc))) > ring.nslot;
+    // In such a long phase the slots go round robin to the warps instead (slot s -> warp s mod 8, the whole slot): with
+    // contiguous runs one warp would own several consecutive slots while the ring delivers them in order, i.e. one warp
+    // would multiply at a time (5b_lyrics, one box: 6 192 us per step round robin, 6 691 us with contiguous runs).
+    const int nslots_phase = (nkk + kpc - 1) >> (31 - __clz(kpc));
+    const bool in_order = !JK_SKIP_FOREIGN_WAIT || nslots_phase > ring.nslot;
+    int slot_i = 0;
 #define JK_MMA_LOOP(NCG)                                                                      \
     {                                                                                         \
-        _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc) {                        \
-            const int a_ = max(kk0, k_lo), b_ = min(min(kk0 + kpc, nkk), k_hi);               \
+        _Pragma("unroll 1") for (int kk0 = 0; kk0 < nkk; kk0 += kpc, ++slot_i) {              \
+            int a_ = max(kk0, k_lo), b_ = min(min(kk0 + kpc, nkk), k_hi);                     \
+            if (in_order) { a_ = kk0; b_ = ((slot_i & 7) == warp) ? min(kk0 + kpc, nkk) : kk0; } \
             if (a_ < b_ || in_order) mbar_wait(ring.full(), ring.phase);                       \
             if (a_ < b_)                                                                      \
                 mma_chunk<NCG>(acc, arow, smem_u32(ring.data()) + lane * 8 + (((a_ - kk0) * NCG) << 8), a_, b_ - a_); \
@@ -540,7 +546,7 @@ __device__ __noinline__ Ring gemm_phase(Ring ring, int B, int epi_, int l, int p
 #undef JK_MMA_LOOP
     STAMP(E, g.pslot, 2);
 #if JK_MMA_ALL_WARPS
-    const int nwarp = min(8, nkk);                                         // warps that multiplied at least one k-step
+    const int nwarp = in_order ? min(8, nslots_phase) : min(8, nkk);       // warps that multiplied at least one k-step
 #else
     const int nwarp = min(8, (nkk + kpc - 1) >> (31 - __clz(kpc)));       // warps that multiplied at least one slot
 #endif

@@ -342,6 +342,17 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             // So the tile goes through shared memory: res_scale * (acc / 2^8 + b2) row by row into the hidden-tile region
             // (free between the k1 conv that just read it and the next tile's hidden tile), then all 128 threads add the
             // residual and store with consecutive lanes on consecutive 16-byte chunks.
+            constexpr int CH4 = C / 4;
+            const int et = tid - 32 * (2 + 4 * kGroups);      // 0..127
+            const float* xin = x + ((size_t)nb * T + t0) * C;
+            // this thread's share of the residual rows (coalesced): the first half is requested before the wait for the k1 conv,
+            // the second while the staged tile settles - off the per-tile chain without spilling (168 registers)
+            float4 xres[CH4];
+#pragma unroll
+            for (int i = 0; i < CH4 / 2; ++i) {
+                const int item = et + i * 128;
+                xres[i] = ((long long)t0 + item / CH4 < T) ? __ldg(reinterpret_cast<const float4*>(xin) + item) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             mbar_wait(&acc2_full[p], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float* stage = reinterpret_cast<float*>(sm + L::offH);      // [128][C] fp32, 16-byte chunks XOR-swizzled with row & 7
@@ -363,18 +374,20 @@ resblock_t5_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc2_empty[p]);
+#pragma unroll
+            for (int i = CH4 / 2; i < CH4; ++i) {
+                const int item = et + i * 128;
+                xres[i] = ((long long)t0 + item / CH4 < T) ? __ldg(reinterpret_cast<const float4*>(xin) + item) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             {
-                constexpr int CH4 = C / 4;
-                const int et = tid - 32 * (2 + 4 * kGroups);      // 0..127
-                const float* xin = x + ((size_t)nb * T + t0) * C;
                 float* xo = out + ((size_t)nb * T + t0) * C;
-#pragma unroll 4
+#pragma unroll
                 for (int i = 0; i < CH4; ++i) {
                     const int item = et + i * 128, rr = item / CH4, jj = item % CH4;
                     if ((long long)t0 + rr < T) {
                         const float4 v = *reinterpret_cast<const float4*>(stage + rr * C + ((jj ^ (rr & 7)) << 2));
-                        const float4 xr = __ldg(reinterpret_cast<const float4*>(xin) + item);
+                        const float4 xr = xres[i];
                         *(reinterpret_cast<float4*>(xo) + item) = make_float4(v.x + xr.x, v.y + xr.y, v.z + xr.z, v.w + xr.w);
                     }
                 }

@@ -9,8 +9,6 @@ echo "smoke rc=$?" >> gpurun_out/j28_status.txt
 tail -1 gpurun_out/j28_smoke.log
 ( time timeout 800 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/j28_bench.json 2> gpurun_out/j28_bench.err ) 2> gpurun_out/j28_bench_time.txt
 cut -c1-300 gpurun_out/j28_bench.json; echo; tail -3 gpurun_out/j28_bench_time.txt
-( time timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/j28_bench_ref.json 2> gpurun_out/j28_bench_ref.err ) 2> gpurun_out/j28_ref_time.txt
-cut -c1-300 gpurun_out/j28_bench_ref.json; echo; tail -3 gpurun_out/j28_ref_time.txt
 timeout 300 python bench.py --workload vqvae_decode --steps 3 --warmup 1 > gpurun_out/j28_bench_vqvae.json 2> gpurun_out/j28_bench_vqvae.err
 cut -c1-200 gpurun_out/j28_bench_vqvae.json; echo
 timeout 300 python tools/vqvae_profile.py > gpurun_out/j28_vqvae_profile.txt 2>&1
