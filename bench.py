@@ -656,10 +656,11 @@ def main():
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = total_bytes / (kern_ms * 1e-3) / 1e9
-    cap = os.path.join(ROOT, "profiles", "ncu_decode_step_full_r02.txt")
+    cap = os.path.join(ROOT, "profiles", "ncu_decode_step_final_p4000_r02.txt")      # the shipped kernel, position 4000
     traffic = None if args.small or args.workload != "1b_lyrics" else ncu_dram_bytes(cap)
     roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                traffic_source="profiles/ncu_decode_step_full_r02.txt (ncu --set full, one launch at position 4000)",
+                traffic_source="profiles/ncu_decode_step_final_p4000_r02.txt (ncu --set full, one launch at position 4000; "
+                               "positions 500 / 8000: ncu_decode_step_final_p500_r02.txt / _p8000_r02.txt)",
                 kernel="jk_decode_step_kernel", launches=len(positions), avg_launch_us=1e3 * kern_ms / len(positions),
                 positions=f"{reps} consecutive launches from each of {octile}",
                 algorithmic_bytes_per_launch=total_bytes / len(positions), weight_bytes_per_launch=w_bytes,
