@@ -605,6 +605,13 @@ def main():
         while state["k"] != 0:
             slice_step()
     # ---- e2e: one full window through the public API with host buffers ---------------------------
+    if world > 1:
+        # NCCL sets a collective up on its first use (hundreds of ms for the first broadcast / gather of a process): a
+        # sampler that runs window after window pays that once, so the two collectives of a window are warmed up here
+        # on dummy rows; the timed window below still does its own scatter and gather
+        with quiet:
+            gather_rows(scatter_rows(torch.zeros(world * n, 4, dtype=torch.long).pin_memory(), n, torch.device("cuda", local)))
+        torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     with quiet:
