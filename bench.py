@@ -481,6 +481,8 @@ def measure_vqvae(args, rank, world, local, steps, warmup, small=False):
                 gpu_launches=int(launches),
                 roofline=dict(bound="hbm", achieved=bytes_plan / t_clip / 1e9, peak=hbm, unit="GB/s",
                               frac=bytes_plan / t_clip / 1e9 / hbm, traffic=traffic,
+                              traffic_source="profiles/ncu_vqvae_resblock_r02.txt: dram bytes of ONE launch of the dominant "
+                                             "kernel, resblock_t5_kernel<64> on [4, 262144, 64] (algorithmic: 537 MB in + out)",
                               note="per-block-fused activation plan 7.3 GB fp32 per clip (SURVEY 8d); compute side: "
                                    "%.1f TFLOP/s achieved of %.0f (bf16 dense peak)" % (flops_clip / t_clip / 1e12, tf)))
 

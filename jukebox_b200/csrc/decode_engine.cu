@@ -62,6 +62,9 @@ using namespace jk;
 #ifndef JK_LOGITS_MMA
 #define JK_LOGITS_MMA 1
 #endif
+#ifndef JK_ATTN_LL_MERGE
+#define JK_ATTN_LL_MERGE 1
+#endif
 
 namespace {
 
@@ -1094,9 +1097,24 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
                         if (d < dh) attn_out_pair(E, b, h, d, r0.x * inv, r0.y * inv, flag);
                         if (d + 8 < dh) attn_out_pair(E, b, h, d + 8, r1.x * inv, r1.y * inv, flag);
                     } else {
+#if JK_ATTN_LL_MERGE
+                        if (last_part) {       // the merging part keeps its own partial in shared memory (osm is free now)
+                            *reinterpret_cast<float2*>(osm + d) = r0;
+                            *reinterpret_cast<float2*>(osm + d + 8) = r1;
+                        } else {               // the others publish theirs as LL words {fp32, flag}
+                            unsigned long long* pl = reinterpret_cast<unsigned long long*>(E->part) +
+                                                     ((size_t)((b * E->H + h) * kMaxSplit + s)) * (dhp + 2) + 2 + d;
+                            const unsigned long long fw = (unsigned long long)flag << 32;
+                            asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(pl), "l"(fw | __float_as_uint(r0.x)),
+                                         "l"(fw | __float_as_uint(r0.y)) : "memory");
+                            asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(pl + 8), "l"(fw | __float_as_uint(r1.x)),
+                                         "l"(fw | __float_as_uint(r1.y)) : "memory");
+                        }
+#else
                         float* part = E->part + ((size_t)((b * E->H + h) * kMaxSplit + s)) * (dhp + 2) + 2;
                         *reinterpret_cast<float2*>(part + d) = r0;
                         *reinterpret_cast<float2*>(part + d + 8) = r1;
+#endif
                     }
                 }
             }
@@ -1105,6 +1123,67 @@ __device__ __noinline__ void attn_item(const LayerDev& LD_ref, int b, int h, int
     }
     STAMP(E, pslot, 3);
     if (ns == 1) return;
+#if JK_ATTN_LL_MERGE
+    // ---- split parts: parts 0 .. ns-2 have published (m, l, o) as LL words; the LAST part (the one that also holds the
+    // current token) polls them and merges - a fixed merger instead of "whoever finishes last": no ticket atomic (an
+    // acq_rel round trip), no second barrier, and the partials arrive word by word like every other hand-over.  Same
+    // order of summation as attn_merge (parts 0 .. ns-1), so the result is bit-identical to the ticket version.
+    {
+        const int item_ = b * E->H + h;
+        unsigned long long* pbase = reinterpret_cast<unsigned long long*>(E->part) + ((size_t)(item_ * kMaxSplit)) * (dhp + 2);
+        if (!last_part) {
+            if (tid == 0) {
+                const unsigned long long fw = (unsigned long long)flag << 32;
+                asm volatile(JK_ST_LL ".v2.u64 [%0], {%1,%2};" ::"l"(pbase + (size_t)s * (dhp + 2)), "l"(fw | __float_as_uint(m_run)),
+                             "l"(fw | __float_as_uint(l_run)) : "memory");
+            }
+            STAMP(E, pslot, 6);
+            return;
+        }
+        consumer_sync();                       // every warp's slice of this part's output is in osm
+        const int d = 2 * tid;
+        if (d < dh) {
+            ulonglong2 ml[3], vv[3];
+            unsigned spins = 0;
+            bool again;
+            do {
+                again = false;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (q < ns - 1) {
+                        ml[q] = ll_ld2(pbase + (size_t)q * (dhp + 2));
+                        vv[q] = ll_ld2(pbase + (size_t)q * (dhp + 2) + 2 + d);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q < ns - 1) again |= !(ll_ok(ml[q].x, flag) && ll_ok(ml[q].y, flag) && ll_ok(vv[q].x, flag) && ll_ok(vv[q].y, flag));
+                if (again) spin_guard(spins);
+            } while (again);
+            float M = m_run;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < ns - 1) M = fmaxf(M, __uint_as_float((uint32_t)ml[q].x));
+            float Lsum = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (q < ns - 1) {
+                    const float w = expf(__uint_as_float((uint32_t)ml[q].x) - M);
+                    Lsum += __uint_as_float((uint32_t)ml[q].y) * w;
+                    o0 += __uint_as_float((uint32_t)vv[q].x) * w; o1 += __uint_as_float((uint32_t)vv[q].y) * w;
+                }
+            }
+            {
+                const float w = expf(m_run - M);
+                const float2 own = *reinterpret_cast<const float2*>(osm + d);
+                Lsum += l_run * w; o0 += own.x * w; o1 += own.y * w;
+            }
+            attn_out_pair(E, b, h, d, o0 / Lsum, o1 / Lsum, flag);
+        }
+        STAMP(E, pslot, 6);
+        return;
+    }
+#endif
     // ---- split parts: the partial is published, the last finisher merges (flash-decoding merge) ------
     const int item = b * E->H + h;
     if (tid == 0) {
@@ -1901,7 +1980,7 @@ int compute_layout(const jk_prior_config& c, int G, Layout& L) {
     L.off_a = off;   off = align_up(off + (size_t)16 * c.n_state * 4, 256);
     L.off_g = off;   off = align_up(off + (size_t)16 * c.mlp_width * 4, 256);
     for (int gi = 0; gi < 4; ++gi) { L.off_xp[gi] = off; off = align_up(off + (size_t)G * 16 * kXpCols * 8, 256); }
-    L.off_part = off; off = align_up(off + (size_t)c.max_batch * c.heads * kMaxSplit * (L.dh_pad + 2) * 4, 256);
+    L.off_part = off; off = align_up(off + (size_t)c.max_batch * c.heads * kMaxSplit * (L.dh_pad + 2) * 8, 256);      // LL words
     L.off_acnt = off; off = align_up(off + (size_t)c.max_batch * c.heads * 4, 256);
     L.off_prof = off; off = align_up(off + (size_t)kProfSlots * 8, 256);
     L.off_prof2 = off; off = align_up(off + (size_t)kProfSlots * 8 * 8, 256);
