@@ -88,3 +88,38 @@ def test_ancestral_sampling_never_prefills(monkeypatch):
     m, eng, drawn = _model(monkeypatch, capacity=512)
     z = m.sample(2, fp16=True, sample_tokens=5)
     assert [c[0] for c in eng.calls] == ["step"] * 5 and drawn == list(range(5)) and z.shape == (2, 5)
+
+
+def test_logit_bias_is_computed_once_per_window_and_passed_to_every_step(monkeypatch):
+    """a prior that adds x_cond behind the stack (autoregressive.py:226-227): x_cond . x_out^T once per window, every step
+    gets it (jkb200.h: jk_step_args.logit_bias) - only when the engine multiplies the logits on the tensor cores"""
+    import jukebox_b200.transformer.f32 as f32
+    for has_gemm in (True, False):
+        m = ar.ConditionalAutoregressive2D((24,), 16, width=64, depth=2, heads=1, attn_order=0, blocks=None, x_cond=True).eval()
+        eng = FakeEngine(512)
+        eng.has_logits_gemm = has_gemm
+        seen = []
+        orig_step = eng.step
+
+        def step(n, logit_bias=None, **kw):
+            seen.append(logit_bias)
+            return orig_step(n, **kw)
+        eng.step = step
+        monkeypatch.setattr(m, "_engine", lambda n: eng)
+        monkeypatch.setattr(m.transformer, "check_cache", lambda *a, **k: None)
+        monkeypatch.setattr(ar, "sample_categorical", lambda logits, temp, seed, position, tokens: None)
+        calls = []
+
+        def fake_linear(x, w):
+            calls.append((tuple(x.shape), tuple(w.shape)))
+            return torch.ones(x.shape[0], w.shape[0])
+        monkeypatch.setattr(f32, "linear_nk", fake_linear)
+        xc = torch.randn(2, 24, 64)
+        m.sample(2, x_cond=xc, fp16=True, sample_tokens=6)
+        assert m.add_cond_after_transformer
+        if has_gemm:
+            assert calls == [((2 * 24, 64), (16, 64))]                       # one GEMM over all positions of the window
+            assert len(seen) == 6 and all(b is not None and tuple(b.shape) == (2, 24, 16) for b in seen)
+            assert all(b is seen[0] for b in seen)
+        else:
+            assert calls == [] and seen == [None] * 6
